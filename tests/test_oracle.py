@@ -1,0 +1,134 @@
+"""Pin the CPU oracle against the reference's own outputs (tests/golden, made by
+make_golden.py from the unmodified reference).  CPU only."""
+
+import numpy as np
+import pytest
+
+from conftest import golden, load_checkpoint, station_latlon
+from oracle import (
+    dense_graph_f64,
+    gcn_gru_forward,
+    gcn_gru_forward_torch,
+    knn_graph_f64,
+    normalised_max_error,
+    synthetic_coordinates,
+)
+from oracle.graph_oracle import dense_to_csr, knn_pattern, mercator
+
+# the fp32 bar is 1e-5 normalised; two fp32 summation orders of the
+# reference itself differ by ~1.3e-6 at S=34.
+TOL_F32 = 1e-5
+TOL_F64 = 1e-12
+
+
+@pytest.mark.parametrize("S", [7, 34])
+def test_graph_bit_exact_vs_reference(S):
+    ref = golden(f"adj_ref_{S}.npy")
+    got = dense_graph_f64(station_latlon(S))
+    assert got.dtype == np.float64
+    assert np.array_equal(got, ref)  # fp64 bit pattern
+    assert np.array_equal(got.astype(np.float32), ref.astype(np.float32))
+
+
+def test_graph_bit_exact_random_coordinates():
+    g = golden("adj_ref_rand50.npz")
+    got = dense_graph_f64(np.stack([g["lat"], g["lon"]], axis=1))
+    assert np.array_equal(got, g["adj"])
+
+
+def test_graph_is_not_bit_symmetric_but_close():
+    a = dense_graph_f64(station_latlon(34))
+    assert np.allclose(a, a.T, rtol=0, atol=1e-15)
+    assert np.all(np.diag(a) > 0)
+
+
+@pytest.mark.parametrize("S", [7, 34])
+def test_forward_fp32_vs_reference(S):
+    g = golden(f"fwd_{S}.npz")
+    adj = golden(f"adj_ref_{S}.npy").astype(np.float32)
+    sd = load_checkpoint(S)
+    y = gcn_gru_forward(adj, g["x"], sd, dtype=np.float32)
+    assert y.shape == g["y_ref_f32"].shape == (g["x"].shape[0], 168, 3 * S)
+    assert normalised_max_error(y, g["y_ref_f32"]) <= TOL_F32
+    yt = gcn_gru_forward_torch(adj, g["x"], sd).numpy()
+    assert normalised_max_error(yt, g["y_ref_f32"]) <= TOL_F32
+
+
+@pytest.mark.parametrize("S", [7, 34])
+def test_forward_fp64_vs_reference_double(S):
+    g = golden(f"fwd_{S}.npz")
+    adj = golden(f"adj_ref_{S}.npy").astype(np.float32).astype(np.float64)
+    y = gcn_gru_forward(adj, g["x"], load_checkpoint(S), dtype=np.float64)
+    assert normalised_max_error(y, g["y_ref_f64"]) <= TOL_F64
+    # the reference's own fp32 rounding noise, for scale (SURVEY: 7.5e-7 / 3.1e-6)
+    assert normalised_max_error(g["y_ref_f32"], g["y_ref_f64"]) <= 1e-5
+
+
+def test_forward_short_windows():
+    g = golden("fwd_34_short.npz")
+    adj = golden("adj_ref_34.npy").astype(np.float32)
+    sd = load_checkpoint(34)
+    for T in (1, 5):
+        y = gcn_gru_forward(adj, g[f"x_T{T}"], sd)
+        assert y.shape == (1, T, 102)
+        assert normalised_max_error(y, g[f"y_T{T}"]) <= TOL_F32
+
+
+def test_forward_non_default_dims():
+    g = golden("fwd_rand.npz")
+    params = {k.replace("__", "."): g[k] for k in g.files if "__" in k}
+    y = gcn_gru_forward(g["adj"], g["x"], params)
+    assert y.shape == (4, 9, 11)
+    assert normalised_max_error(y, g["y_ref_f32"]) <= TOL_F32
+
+
+def test_batch_independence():
+    g = golden("fwd_7.npz")
+    adj = golden("adj_ref_7.npy").astype(np.float32)
+    sd = load_checkpoint(7)
+    full = gcn_gru_forward(adj, g["x"], sd, dtype=np.float64)
+    for b in range(g["x"].shape[0]):
+        one = gcn_gru_forward(adj, g["x"][b : b + 1], sd, dtype=np.float64)
+        # BLAS picks different blockings for different batch sizes -> not bit-equal
+        assert normalised_max_error(one[0], full[b]) <= TOL_F64
+
+
+def test_synthetic_coordinates_deterministic_and_in_box():
+    c = synthetic_coordinates(4096, seed=0)
+    assert c.shape == (4096, 2)
+    assert np.array_equal(c, synthetic_coordinates(4096, seed=0))
+    assert not np.array_equal(c[:16], synthetic_coordinates(16, seed=1))
+    assert np.array_equal(c[:16], synthetic_coordinates(16, seed=0))  # prefix-stable
+    assert c[:, 0].min() >= 50.10 and c[:, 0].max() <= 51.59
+    assert c[:, 1].min() >= -113.36 and c[:, 1].max() <= -110.09
+    # known answers (SplitMix64, seed 0: first output 0xE220A8397B1DCDAF)
+    u0 = (0xE220A8397B1DCDAF >> 11) * 2.0**-53
+    assert c[0, 0] == 50.10 + u0 * (51.59 - 50.10)
+
+
+def test_knn_graph_properties():
+    S, k = 96, 8
+    latlon = synthetic_coordinates(S, seed=3)
+    a = knn_graph_f64(latlon, k)
+    dense = dense_graph_f64(latlon)
+    nz = a != 0
+    assert np.array_equal(nz, nz.T)  # symmetric pattern
+    deg = nz.sum(axis=1)
+    assert deg.min() >= k + 1  # k neighbours + self loop
+    # un-normalised weights are the dense ones on the pattern: ratio of two entries in
+    # one row/col pair is preserved only through d, so check via the pattern + the k
+    # nearest by distance being present
+    xy = mercator(latlon)
+    d2 = ((xy[:, None, :] - xy[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d2, np.inf)
+    for i in range(S):
+        nearest = np.argsort(d2[i], kind="stable")[:k]
+        assert nz[i, nearest].all()
+    indptr, indices, vals = dense_to_csr(a)
+    assert indptr[-1] == nz.sum() == len(indices) == len(vals)
+    assert dense.shape == a.shape
+    # k >= S-1 degenerates to the dense reference graph, bit for bit
+    assert np.array_equal(knn_graph_f64(latlon[:9], 8), dense_graph_f64(latlon[:9]))
+    m = knn_pattern(np.array([[0.0, 1.0, 1.0], [1.0, 0.0, 4.0], [1.0, 4.0, 0.0]]), 1)
+    # ties broken by lower index: node 0 picks 1; 1 picks 0; 2 picks 0
+    assert m.tolist() == [[True, True, True], [True, True, False], [True, False, True]]
