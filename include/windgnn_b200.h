@@ -1,0 +1,154 @@
+/*
+ * windgnn_b200.h — C-ABI of the B200-native WindGNN forward hot path.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes plain
+ * pointers and sizes (no torch / C++ types) and names the reference interface it
+ * replaces.  Reference paths are relative to NagsTheProgrammer/WindGNN.
+ *
+ * Conventions
+ *   - All tensors are dense, row-major ("C-contiguous") fp32 unless stated.
+ *   - "device pointer" = memory of CUDA device `device`; the call is asynchronous
+ *     on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *   - The caller owns every buffer, including `workspace`; the library keeps no
+ *     pointer after the call returns and has no global mutable state besides the
+ *     thread-local last-error string.
+ *   - Return value: 0 (WG_OK) on success, a negative WG_ERR_* code otherwise;
+ *     `wg_last_error()` then describes the failure.  Nothing throws.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point
+ *     returns WG_ERR_CUDA.
+ */
+#ifndef WINDGNN_B200_H
+#define WINDGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WG_ABI_VERSION 1
+
+enum {
+    WG_OK = 0,
+    WG_ERR_BAD_ARG = -1,     /* null pointer, non-positive size, inconsistent dims        */
+    WG_ERR_UNSUPPORTED = -2, /* dims outside what the sm_100a kernels are built for       */
+    WG_ERR_WORKSPACE = -3,   /* workspace too small or misaligned (needs 256 B alignment) */
+    WG_ERR_CUDA = -4         /* CUDA runtime error (message holds cudaGetErrorString)     */
+};
+
+/* Library / ABI identification. */
+int wg_abi_version(void);
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char* wg_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * GCN-GRU forward — replaces `GCN_GRU.forward(adj_matrix, attr_matrix)`
+ * (src/step6_gcn_gru_combined_model.py:13-27; called at src/main.py:66,102), i.e.
+ *   conv1 -> conv2 (src/step5_gcn_layer_model.py:13-23) -> flatten [T, S*F_out]
+ *   -> nn.GRU(batch_first, h0 = 0) -> every hidden state.
+ *
+ *   adj   [S, S]                 normalised adjacency (src/step2_graph_builder.py:38 -> main.py:26)
+ *   x     [B, T, S, F_in]        step4 window layout (src/step4_sequence_preparer.py:13)
+ *   w1    [F_in, F_hid], b1 [F_hid]      conv1.weight / conv1.bias   (in x out, not transposed)
+ *   w2    [F_hid, F_out], b2 [F_out]     conv2.weight / conv2.bias
+ *   w_ih  [3H, S*F_out]          gru.weight_ih_l0  (gate rows r, z, n)
+ *   w_hh  [3H, H]                gru.weight_hh_l0
+ *   b_ih  [3H], b_hh [3H]        gru.bias_ih_l0 / gru.bias_hh_l0
+ *   out   [B, T, H]              (the reference, batch 1 only, returns out[0])
+ *
+ * The reference accepts B == 1 only (step6:20); this entry point is batch-generalised:
+ * sequences are independent (h0 = 0 for each).
+ *
+ * `chunk` = sequences processed per internal pass (bounds the workspace); 0 = default.
+ * ---------------------------------------------------------------------------------- */
+size_t wg_gcn_gru_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
+                                  int64_t chunk);
+
+int wg_gcn_gru_forward_f32(const float* adj, const float* x, const float* w1, const float* b1,
+                           const float* w2, const float* b2, const float* w_ih, const float* w_hh,
+                           const float* b_ih, const float* b_hh, float* out, int64_t B, int T, int S,
+                           int F_in, int F_hid, int F_out, int H, int64_t chunk, void* workspace,
+                           size_t workspace_bytes, int device, void* stream);
+
+/* Same computation with HOST buffers for x (pinned for full overlap) and out: the batch is
+ * streamed through the device in `chunk`-sized pieces, H2D copy / compute / D2H copy of
+ * consecutive pieces overlapped on internal streams.  Parameters and adj are device
+ * pointers (they are the model, resident on the GPU as in src/main.py:27,43).  Blocks
+ * until `out_host` is complete.  Replaces the per-window loop of src/main.py:101-103
+ * (`model(adj, batch_x)` followed by `.cpu()`). */
+size_t wg_gcn_gru_host_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
+                                       int64_t chunk);
+
+int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const float* w1,
+                                const float* b1, const float* w2, const float* b2,
+                                const float* w_ih, const float* w_hh, const float* b_ih,
+                                const float* b_hh, float* out_host, int64_t B, int T, int S,
+                                int F_in, int F_hid, int F_out, int H, int64_t chunk,
+                                void* workspace, size_t workspace_bytes, int device);
+
+/* ------------------------------------------------------------------------------------
+ * Single GCN layer — replaces `GraphConvLayer.forward(adj_matrix, attr_matrix)`
+ * (src/step5_gcn_layer_model.py:13-23):  out = relu((adj @ attr) @ weight + bias).
+ *   attr [R, S, F_in] (R = product of the leading dims),  out [R, S, F_out].
+ * No workspace.
+ * ---------------------------------------------------------------------------------- */
+int wg_gcn_layer_f32(const float* adj, const float* attr, const float* weight, const float* bias,
+                     float* out, int64_t R, int S, int F_in, int F_out, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Stage entry points (the three kernels wg_gcn_gru_forward_f32 chains).  Exposed so the
+ * benchmark can time, and the tests can check, each kernel alone.  `workspace` must have
+ * been sized by wg_gcn_gru_workspace_bytes for the same dims and must already hold the
+ * packed parameters (wg_stage_pack_f32) before stages 2 and 3.
+ *   stage_pack  : re-lay w_ih / w_hh / biases for the kernels
+ *   stage_gcn   : x [Bc,T,S,F_in] -> U [Bc*T, IP]        (two GCN layers, fused)
+ *   stage_inproj: U -> GI [Bc*T, GP] = U . w_ih^T + b     (the GRU input projection)
+ *   stage_recur : GI -> out [Bc,T,H]                      (the serial GRU recurrence)
+ * Bc must be <= the chunk the workspace was sized for.
+ * ---------------------------------------------------------------------------------- */
+int wg_stage_pack_f32(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                      int T, int S, int F_in, int F_hid, int F_out, int H, int64_t chunk,
+                      void* workspace, size_t workspace_bytes, int device, void* stream);
+int wg_stage_gcn_f32(const float* adj, const float* x, const float* w1, const float* b1,
+                     const float* w2, const float* b2, int64_t Bc, int T, int S, int F_in, int F_hid,
+                     int F_out, int H, int64_t chunk, void* workspace, size_t workspace_bytes,
+                     int device, void* stream);
+int wg_stage_inproj_f32(int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H,
+                        int64_t chunk, void* workspace, size_t workspace_bytes, int device,
+                        void* stream);
+int wg_stage_recur_f32(float* out, int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H,
+                       int64_t chunk, void* workspace, size_t workspace_bytes, int device,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Graph build — replaces `build_graph(df)` after its Mercator step
+ * (src/step2_graph_builder.py:16-40; the libm log/tan of :8-13 stay on the host).
+ *   xy        [S, 2] fp64 device pointer: (northing, easting) metres per station
+ *   adj_f64   [S, S] fp64 out (may be NULL)   D^-1/2 (A+I) D^-1/2, bit-identical to SciPy's
+ *             evaluation order
+ *   adj_f32   [S, S] fp32 out (may be NULL)   the `.float()` cast of src/main.py:26
+ *   k         0 = dense reference graph; k > 0 = symmetrised k-nearest-neighbour pattern
+ *             (edge (i,j) kept iff j in kNN(i) or i in kNN(j); ties -> smaller index), the
+ *             synthetic large-graph generator.  Same weights and normalisation.
+ *   workspace device scratch of wg_build_graph_workspace_bytes(S, k) bytes.
+ * ---------------------------------------------------------------------------------- */
+size_t wg_build_graph_workspace_bytes(int S, int k);
+int wg_build_graph_f64(const double* xy, double* adj_f64, float* adj_f32, int S, int k,
+                       void* workspace, size_t workspace_bytes, int device, void* stream);
+
+/* Deterministic synthetic station coordinates (SplitMix64 stream):
+ *   latlon [S, 2] fp64 device out, uniform in the shipped stations' bounding box. */
+int wg_synthetic_coordinates_f64(double* latlon, int S, uint64_t seed, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Measurement helper: sustained FP32 FFMA throughput of this device in TFLOP/s (2 flops per
+ * FFMA), measured with CUDA events over `iters` launches of a register-resident FFMA loop.
+ * Used by bench.py as the FP32 roofline denominator.  Returns < 0 on error.
+ * ---------------------------------------------------------------------------------- */
+double wg_measure_ffma_tflops(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WINDGNN_B200_H */

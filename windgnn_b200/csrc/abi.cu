@@ -1,0 +1,535 @@
+// C-ABI of the WindGNN B200 forward path (see include/windgnn_b200.h).
+// Host side: argument validation, workspace planning, kernel dispatch.  No torch, no state.
+
+#include "../../include/windgnn_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "gcn.cuh"
+#include "inproj.cuh"
+#include "recur.cuh"
+#include "wg_common.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define WG_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(WG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// RAII device switch (the caller's current device is restored on return).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+constexpr size_t kAlign = 256;
+size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+// Everything the three stages need to agree on.
+struct Plan {
+    int T, S, Fi, Fh, Fo, H;
+    long long chunk;
+    int I, G;      // S*Fo, 3H
+    int IP;        // K of the projection GEMM: I rounded up to 16
+    int NPB;       // rows of packed w_ih: G rounded up to 64
+    int GP;        // leading dim of GI: G rounded up to 4
+    int KP;        // K of the recurrent GEMM: H rounded up to 4
+    int NPR;       // columns of packed w_hh^T: G rounded up to 32
+    size_t off_wp, off_bias, off_wht, off_bhn, off_u, off_gi, total;
+};
+
+long long default_chunk(long long B) {
+    const long long one_wave = (long long)wg::kNumSMs * wg::kRcBT;  // 4736 sequences
+    return B < one_wave ? (B < 1 ? 1 : B) : one_wave;
+}
+
+int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H, long long chunk) {
+    if (B < 0 || T <= 0 || S <= 0 || Fi <= 0 || Fh <= 0 || Fo <= 0 || H <= 0 || chunk < 0)
+        return fail(WG_ERR_BAD_ARG, "non-positive dimension (B=%lld T=%d S=%d F=%d/%d/%d H=%d chunk=%lld)",
+                    B, T, S, Fi, Fh, Fo, H, chunk);
+    if ((long long)S * Fo > (1 << 20) || H > (1 << 15))
+        return fail(WG_ERR_UNSUPPORTED, "dimension too large (S*F_out=%lld, H=%d)", (long long)S * Fo, H);
+    p.T = T; p.S = S; p.Fi = Fi; p.Fh = Fh; p.Fo = Fo; p.H = H;
+    p.chunk = chunk > 0 ? chunk : default_chunk(B);
+    if (p.chunk > B && B > 0) p.chunk = B;
+    p.I = S * Fo;
+    p.G = 3 * H;
+    p.IP = wg::round_up(p.I, wg::kIpBK);
+    p.NPB = wg::round_up(p.G, wg::kIpBN);
+    p.GP = wg::round_up(p.G, 4);
+    p.KP = wg::round_up(H, 4);
+    p.NPR = wg::round_up(p.G, 32);
+    size_t o = 0;
+    p.off_wp = o;   o = align_up(o + (size_t)p.NPB * p.IP * 4);
+    p.off_bias = o; o = align_up(o + (size_t)p.NPB * 4);
+    p.off_wht = o;  o = align_up(o + (size_t)p.KP * p.NPR * 4);
+    p.off_bhn = o;  o = align_up(o + (size_t)p.KP * 4);
+    const size_t rows = (size_t)p.chunk * T;
+    p.off_u = o;    o = align_up(o + rows * p.IP * 4);
+    p.off_gi = o;   o = align_up(o + rows * p.GP * 4);
+    p.total = o;
+    return WG_OK;
+}
+
+int check_ws(const Plan& p, const void* ws, size_t bytes) {
+    if (!ws) return fail(WG_ERR_WORKSPACE, "workspace is NULL (need %zu bytes)", p.total);
+    if (reinterpret_cast<uintptr_t>(ws) % kAlign)
+        return fail(WG_ERR_WORKSPACE, "workspace must be %zu-byte aligned", kAlign);
+    if (bytes < p.total)
+        return fail(WG_ERR_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", bytes, p.total);
+    return WG_OK;
+}
+
+template <typename T>
+T* ws_ptr(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+
+// ---------------------------------------------------------------------------------------------
+// parameter packing (tiny; runs every call so the library stays stateless)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_params_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                   const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                   float* __restrict__ wp, float* __restrict__ bias,
+                                   float* __restrict__ wht, float* __restrict__ bhn, int I, int H, int IP,
+                                   int NPB, int KP, int NPR) {
+    const int G = 3 * H;
+    const long long n_wp = (long long)NPB * IP;
+    const long long n_wht = (long long)KP * NPR;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long e = t0; e < n_wp; e += stride) {
+        const int n = (int)(e / IP), k = (int)(e % IP);
+        wp[e] = (n < G && k < I) ? w_ih[(size_t)n * I + k] : 0.0f;
+    }
+    for (long long e = t0; e < n_wht; e += stride) {
+        const int k = (int)(e / NPR), n = (int)(e % NPR);
+        wht[e] = (k < H && n < G) ? w_hh[(size_t)n * H + k] : 0.0f;
+    }
+    for (long long e = t0; e < NPB; e += stride) {
+        float v = 0.0f;
+        if (e < G) v = b_ih[e] + (e < 2 * H ? b_hh[e] : 0.0f);  // r,z: both biases; n: b_in only
+        bias[e] = v;
+    }
+    for (long long e = t0; e < KP; e += stride) bhn[e] = e < H ? b_hh[2 * H + e] : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage launchers
+// ---------------------------------------------------------------------------------------------
+template <int FP, int SG, bool EXACT, int LAYERS>
+int launch_gcn_t(const float* X, const float* adj, const float* W1, const float* b1, const float* W2,
+                 const float* b2, float* out, long long R, int S, int Fi, int Fh, int Fo, int ldo,
+                 cudaStream_t st) {
+    const int NSG = wg::ceil_div(S, SG);
+    if (NSG > wg::kGcnThreads)
+        return fail(WG_ERR_UNSUPPORTED, "S=%d too large for the dense GCN kernel", S);
+    int RB = wg::kGcnThreads / NSG;
+    size_t smem = wg::gcn_smem_floats<FP, SG>(S, Fi, Fh, Fo, RB, LAYERS) * 4;
+    while (smem > (size_t)wg::kMaxSmemOptin && RB > 1) {
+        RB = RB / 2;
+        smem = wg::gcn_smem_floats<FP, SG>(S, Fi, Fh, Fo, RB, LAYERS) * 4;
+    }
+    // keep >= 2 CTAs per SM resident when the slabs allow it
+    while (smem > (size_t)wg::kMaxSmemOptin / 2 && RB > 8) {
+        RB = RB - RB / 4;
+        smem = wg::gcn_smem_floats<FP, SG>(S, Fi, Fh, Fo, RB, LAYERS) * 4;
+    }
+    if (smem > (size_t)wg::kMaxSmemOptin)
+        return fail(WG_ERR_UNSUPPORTED, "dense GCN needs %zu B of shared memory (S=%d); use the sparse path", smem, S);
+    auto kern = wg::gcn_kernel<FP, SG, EXACT, LAYERS>;
+    WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    WG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wg::kGcnThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long nblocks = (R + RB - 1) / RB;
+    long long grid = (long long)wg::kNumSMs * per_sm;
+    if (grid > nblocks) grid = nblocks;
+    if (grid < 1) return WG_OK;
+    kern<<<(unsigned)grid, wg::kGcnThreads, smem, st>>>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, RB);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+template <int LAYERS>
+int launch_gcn(const float* X, const float* adj, const float* W1, const float* b1, const float* W2,
+               const float* b2, float* out, long long R, int S, int Fi, int Fh, int Fo, int ldo,
+               cudaStream_t st) {
+    const int fmax = Fi > Fh ? (Fi > Fo ? Fi : Fo) : (Fh > Fo ? Fh : Fo);
+    if (Fi == 13 && Fh == 13 && Fo == 13)
+        return launch_gcn_t<13, 7, true, LAYERS>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, st);
+    if (fmax <= 16)
+        return launch_gcn_t<16, 4, false, LAYERS>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, st);
+    return fail(WG_ERR_UNSUPPORTED, "GCN feature width %d > 16 is not built into the dense kernel", fmax);
+}
+
+int launch_inproj(const Plan& p, void* ws, long long rows, cudaStream_t st) {
+    const long long m_tiles = (rows + wg::kIpBM - 1) / wg::kIpBM;
+    const int n_tiles = p.NPB / wg::kIpBN;
+    const long long grid = m_tiles * n_tiles;
+    if (grid < 1) return WG_OK;
+    if (grid > 0x7fffffffLL) return fail(WG_ERR_UNSUPPORTED, "projection grid too large");
+    WG_CUDA(cudaFuncSetAttribute(wg::inproj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 wg::kIpSmemBytes));
+    wg::inproj_kernel<<<(unsigned)grid, wg::kIpThreads, wg::kIpSmemBytes, st>>>(
+        ws_ptr<float>(ws, p.off_u), ws_ptr<float>(ws, p.off_wp), ws_ptr<float>(ws, p.off_bias),
+        ws_ptr<float>(ws, p.off_gi), rows, p.G, p.IP, p.GP, n_tiles);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+template <int NW, bool WS>
+int launch_recur_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
+    const size_t smem = wg::recur_smem_floats(p.KP, p.NPR, WS) * 4;
+    auto kern = wg::gru_recur_kernel<NW, WS>;
+    WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (Bc + wg::kRcBT - 1) / wg::kRcBT;
+    if (grid < 1) return WG_OK;
+    kern<<<(unsigned)grid, NW * 32, smem, st>>>(ws_ptr<float>(ws, p.off_gi), ws_ptr<float>(ws, p.off_wht),
+                                               ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, p.GP,
+                                               p.KP, p.NPR);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+template <bool WS>
+int launch_recur_ws(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
+    const int tiles = 2 * (p.NPR / 32);
+    const int for_gates = wg::ceil_div(wg::kRcBT * p.H, wg::kRcMaxQ * 32);
+    int need = tiles < 32 ? tiles : 32;
+    if (for_gates > need) need = for_gates;
+    if (need <= 4) return launch_recur_t<4, WS>(p, ws, out, Bc, st);
+    if (need <= 8) return launch_recur_t<8, WS>(p, ws, out, Bc, st);
+    if (need <= 12) return launch_recur_t<12, WS>(p, ws, out, Bc, st);
+    if (need <= 16) return launch_recur_t<16, WS>(p, ws, out, Bc, st);
+    if (need <= 20) return launch_recur_t<20, WS>(p, ws, out, Bc, st);
+    if (need <= 24) return launch_recur_t<24, WS>(p, ws, out, Bc, st);
+    if (need <= 32) return launch_recur_t<32, WS>(p, ws, out, Bc, st);
+    return fail(WG_ERR_UNSUPPORTED, "GRU hidden size %d too large for the recurrence kernel (max %d)",
+                p.H, wg::kRcMaxQ * 1024 / wg::kRcBT);
+}
+
+int launch_recur(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
+    const size_t smem_ws = wg::recur_smem_floats(p.KP, p.NPR, true) * 4;
+    if (smem_ws <= (size_t)wg::kMaxSmemOptin) return launch_recur_ws<true>(p, ws, out, Bc, st);
+    const size_t smem_nows = wg::recur_smem_floats(p.KP, p.NPR, false) * 4;
+    if (smem_nows <= (size_t)wg::kMaxSmemOptin) return launch_recur_ws<false>(p, ws, out, Bc, st);
+    return fail(WG_ERR_UNSUPPORTED, "GRU hidden size %d: state does not fit shared memory", p.H);
+}
+
+int launch_pack(const Plan& p, void* ws, const float* w_ih, const float* w_hh, const float* b_ih,
+                const float* b_hh, cudaStream_t st) {
+    pack_params_kernel<<<wg::kNumSMs * 2, 256, 0, st>>>(
+        w_ih, w_hh, b_ih, b_hh, ws_ptr<float>(ws, p.off_wp), ws_ptr<float>(ws, p.off_bias),
+        ws_ptr<float>(ws, p.off_wht), ws_ptr<float>(ws, p.off_bhn), p.I, p.H, p.IP, p.NPB, p.KP, p.NPR);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+// One chunk (Bc <= plan.chunk sequences) through the three stages.
+int run_chunk(const Plan& p, void* ws, const float* adj, const float* x, const float* w1, const float* b1,
+              const float* w2, const float* b2, float* out, long long Bc, cudaStream_t st) {
+    const long long rows = Bc * p.T;
+    int rc = launch_gcn<2>(x, adj, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_u), rows, p.S, p.Fi, p.Fh, p.Fo,
+                           p.IP, st);
+    if (rc) return rc;
+    rc = launch_inproj(p, ws, rows, st);
+    if (rc) return rc;
+    return launch_recur(p, ws, out, Bc, st);
+}
+
+bool any_null(std::initializer_list<const void*> ps) {
+    for (const void* q : ps)
+        if (!q) return true;
+    return false;
+}
+
+// FFMA peak microbenchmark: 8 independent chains per thread, register resident.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* sink, int iters, float a, float b) {
+    float v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6,
+          v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            v0 = fmaf(v0, a, b); v1 = fmaf(v1, a, b); v2 = fmaf(v2, a, b); v3 = fmaf(v3, a, b);
+            v4 = fmaf(v4, a, b); v5 = fmaf(v5, a, b); v6 = fmaf(v6, a, b); v7 = fmaf(v7, a, b);
+        }
+    }
+    const float s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+    if (s == 123.456f) sink[0] = s;  // never true in practice; keeps the chains alive
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int wg_abi_version(void) { return WG_ABI_VERSION; }
+// used by graph.cu (separate translation unit, built with -fmad=false) to set the error text
+int wg_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+const char* wg_last_error(void) { return g_err; }
+
+size_t wg_gcn_gru_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
+                                  int64_t chunk) {
+    Plan p;
+    if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk)) return 0;
+    return p.total;
+}
+
+int wg_stage_pack_f32(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int T,
+                      int S, int F_in, int F_hid, int F_out, int H, int64_t chunk, void* workspace,
+                      size_t workspace_bytes, int device, void* stream) {
+    if (any_null({w_ih, w_hh, b_ih, b_hh})) return fail(WG_ERR_BAD_ARG, "null parameter pointer");
+    Plan p;
+    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk);
+    if (rc) return rc;
+    if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    return launch_pack(p, workspace, w_ih, w_hh, b_ih, b_hh, static_cast<cudaStream_t>(stream));
+}
+
+int wg_stage_gcn_f32(const float* adj, const float* x, const float* w1, const float* b1, const float* w2,
+                     const float* b2, int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H,
+                     int64_t chunk, void* workspace, size_t workspace_bytes, int device, void* stream) {
+    if (any_null({adj, x, w1, b1, w2, b2})) return fail(WG_ERR_BAD_ARG, "null pointer");
+    Plan p;
+    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk);
+    if (rc) return rc;
+    if (Bc < 0 || Bc > p.chunk) return fail(WG_ERR_BAD_ARG, "Bc=%lld outside [0, chunk=%lld]", (long long)Bc, p.chunk);
+    if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    return launch_gcn<2>(x, adj, w1, b1, w2, b2, ws_ptr<float>(workspace, p.off_u), (long long)Bc * T, S,
+                         F_in, F_hid, F_out, p.IP, static_cast<cudaStream_t>(stream));
+}
+
+int wg_stage_inproj_f32(int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H, int64_t chunk,
+                        void* workspace, size_t workspace_bytes, int device, void* stream) {
+    Plan p;
+    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk);
+    if (rc) return rc;
+    if (Bc < 0 || Bc > p.chunk) return fail(WG_ERR_BAD_ARG, "Bc=%lld outside [0, chunk=%lld]", (long long)Bc, p.chunk);
+    if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    return launch_inproj(p, workspace, (long long)Bc * T, static_cast<cudaStream_t>(stream));
+}
+
+int wg_stage_recur_f32(float* out, int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H,
+                       int64_t chunk, void* workspace, size_t workspace_bytes, int device, void* stream) {
+    if (!out) return fail(WG_ERR_BAD_ARG, "null output pointer");
+    Plan p;
+    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk);
+    if (rc) return rc;
+    if (Bc < 0 || Bc > p.chunk) return fail(WG_ERR_BAD_ARG, "Bc=%lld outside [0, chunk=%lld]", (long long)Bc, p.chunk);
+    if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    return launch_recur(p, workspace, out, Bc, static_cast<cudaStream_t>(stream));
+}
+
+int wg_gcn_gru_forward_f32(const float* adj, const float* x, const float* w1, const float* b1,
+                           const float* w2, const float* b2, const float* w_ih, const float* w_hh,
+                           const float* b_ih, const float* b_hh, float* out, int64_t B, int T, int S,
+                           int F_in, int F_hid, int F_out, int H, int64_t chunk, void* workspace,
+                           size_t workspace_bytes, int device, void* stream) {
+    Plan p;
+    int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk);
+    if (rc) return rc;
+    if (B == 0) return WG_OK;
+    if (any_null({adj, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, out}))
+        return fail(WG_ERR_BAD_ARG, "null pointer argument");
+    if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_pack(p, workspace, w_ih, w_hh, b_ih, b_hh, st))) return rc;
+    const size_t x_seq = (size_t)T * S * F_in, o_seq = (size_t)T * H;
+    for (long long b0 = 0; b0 < B; b0 += p.chunk) {
+        const long long Bc = (B - b0) < p.chunk ? (B - b0) : p.chunk;
+        rc = run_chunk(p, workspace, adj, x + (size_t)b0 * x_seq, w1, b1, w2, b2, out + (size_t)b0 * o_seq,
+                       Bc, st);
+        if (rc) return rc;
+    }
+    return WG_OK;
+}
+
+// ---- host-buffer variant: H2D / compute / D2H of consecutive chunks overlapped ----------------
+// workspace = [ compute workspace | x staging 0 | x staging 1 | out staging 0 | out staging 1 ]
+size_t wg_gcn_gru_host_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
+                                       int64_t chunk) {
+    Plan p;
+    if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk)) return 0;
+    const size_t xs = align_up((size_t)p.chunk * T * S * F_in * 4);
+    const size_t os = align_up((size_t)p.chunk * T * H * 4);
+    return p.total + 2 * xs + 2 * os;
+}
+
+int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const float* w1, const float* b1,
+                                const float* w2, const float* b2, const float* w_ih, const float* w_hh,
+                                const float* b_ih, const float* b_hh, float* out_host, int64_t B, int T,
+                                int S, int F_in, int F_hid, int F_out, int H, int64_t chunk,
+                                void* workspace, size_t workspace_bytes, int device) {
+    Plan p;
+    int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk);
+    if (rc) return rc;
+    if (B == 0) return WG_OK;
+    if (any_null({adj, x_host, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, out_host}))
+        return fail(WG_ERR_BAD_ARG, "null pointer argument");
+    const size_t xs = align_up((size_t)p.chunk * T * S * F_in * 4);
+    const size_t os = align_up((size_t)p.chunk * T * H * 4);
+    if (!workspace || reinterpret_cast<uintptr_t>(workspace) % kAlign)
+        return fail(WG_ERR_WORKSPACE, "workspace NULL or not %zu-byte aligned", kAlign);
+    if (workspace_bytes < p.total + 2 * xs + 2 * os)
+        return fail(WG_ERR_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", workspace_bytes,
+                    p.total + 2 * xs + 2 * os);
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+
+    char* base = static_cast<char*>(workspace);
+    float* xdev[2] = {reinterpret_cast<float*>(base + p.total), reinterpret_cast<float*>(base + p.total + xs)};
+    float* odev[2] = {reinterpret_cast<float*>(base + p.total + 2 * xs),
+                      reinterpret_cast<float*>(base + p.total + 2 * xs + os)};
+
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    int result = WG_OK;
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; ++i) {
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_cmp[i]) cudaEventDestroy(ev_cmp[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_cmp) cudaStreamDestroy(s_cmp);
+        if (s_out) cudaStreamDestroy(s_out);
+    };
+#define WG_CUDA_H(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            result = fail(WG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),  \
+                          __FILE__, __LINE__);                                                  \
+            cudaDeviceSynchronize();                                                            \
+            cleanup();                                                                          \
+            return result;                                                                      \
+        }                                                                                       \
+    } while (0)
+
+    WG_CUDA_H(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    WG_CUDA_H(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+    WG_CUDA_H(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        WG_CUDA_H(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+        WG_CUDA_H(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming));
+        WG_CUDA_H(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+    }
+    if ((rc = launch_pack(p, workspace, w_ih, w_hh, b_ih, b_hh, s_cmp))) {
+        cudaDeviceSynchronize();
+        cleanup();
+        return rc;
+    }
+    const size_t x_seq = (size_t)T * S * F_in, o_seq = (size_t)T * H;
+    long long n_chunks = (B + p.chunk - 1) / p.chunk;
+    for (long long c = 0; c < n_chunks; ++c) {
+        const int sl = (int)(c & 1);
+        const long long b0 = c * p.chunk;
+        const long long Bc = (B - b0) < p.chunk ? (B - b0) : p.chunk;
+        // x staging slot is free once the compute that read it (chunk c-2) is done
+        if (c >= 2) WG_CUDA_H(cudaStreamWaitEvent(s_in, ev_cmp[sl], 0));
+        WG_CUDA_H(cudaMemcpyAsync(xdev[sl], x_host + (size_t)b0 * x_seq, (size_t)Bc * x_seq * 4,
+                                  cudaMemcpyHostToDevice, s_in));
+        WG_CUDA_H(cudaEventRecord(ev_in[sl], s_in));
+        // compute waits for its input and for the D2H that last used this out slot (chunk c-2)
+        WG_CUDA_H(cudaStreamWaitEvent(s_cmp, ev_in[sl], 0));
+        if (c >= 2) WG_CUDA_H(cudaStreamWaitEvent(s_cmp, ev_out[sl], 0));
+        if ((rc = run_chunk(p, workspace, adj, xdev[sl], w1, b1, w2, b2, odev[sl], Bc, s_cmp))) {
+            cudaDeviceSynchronize();
+            cleanup();
+            return rc;
+        }
+        WG_CUDA_H(cudaEventRecord(ev_cmp[sl], s_cmp));
+        WG_CUDA_H(cudaStreamWaitEvent(s_out, ev_cmp[sl], 0));
+        WG_CUDA_H(cudaMemcpyAsync(out_host + (size_t)b0 * o_seq, odev[sl], (size_t)Bc * o_seq * 4,
+                                  cudaMemcpyDeviceToHost, s_out));
+        WG_CUDA_H(cudaEventRecord(ev_out[sl], s_out));
+    }
+    WG_CUDA_H(cudaStreamSynchronize(s_out));
+    WG_CUDA_H(cudaStreamSynchronize(s_cmp));
+    WG_CUDA_H(cudaStreamSynchronize(s_in));
+#undef WG_CUDA_H
+    cleanup();
+    return WG_OK;
+}
+
+int wg_gcn_layer_f32(const float* adj, const float* attr, const float* weight, const float* bias,
+                     float* out, int64_t R, int S, int F_in, int F_out, int device, void* stream) {
+    if (R < 0 || S <= 0 || F_in <= 0 || F_out <= 0)
+        return fail(WG_ERR_BAD_ARG, "non-positive dimension (R=%lld S=%d F=%d/%d)", (long long)R, S, F_in, F_out);
+    if (R == 0) return WG_OK;
+    if (any_null({adj, attr, weight, bias, out})) return fail(WG_ERR_BAD_ARG, "null pointer argument");
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    // single layer: "hidden" plays the role of the output width
+    return launch_gcn<1>(attr, adj, weight, bias, nullptr, nullptr, out, R, S, F_in, F_out, F_out,
+                         S * F_out, static_cast<cudaStream_t>(stream));
+}
+
+double wg_measure_ffma_tflops(int device, int iters) {
+    DeviceGuard g(device);
+    if (g.err != cudaSuccess) {
+        fail(WG_ERR_CUDA, "cudaSetDevice failed: %s", cudaGetErrorString(g.err));
+        return -1.0;
+    }
+    if (iters < 1) iters = 1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8;  // 8 x 256 threads = 64 warps per SM
+    const int loop = 4096;
+    float* sink = nullptr;
+    if (cudaMalloc(&sink, 4) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    ffma_peak_kernel<<<blocks, 256>>>(sink, loop, 0.999f, 0.001f);  // warm-up
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) ffma_peak_kernel<<<blocks, 256>>>(sink, loop, 0.999f, 0.001f);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (e != cudaSuccess || ms <= 0.f) {
+        fail(WG_ERR_CUDA, "ffma microbenchmark failed: %s", cudaGetErrorString(e));
+        return -1.0;
+    }
+    const double flops = 2.0 * 8 * 16 * (double)loop * 256.0 * blocks * iters;
+    return flops / (ms * 1e-3) / 1e12;
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// Shared helpers for the WindGNN B200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace wg {
+
+__host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+constexpr int kNumSMs = 148;        // B200: 2 dies x 74 SMs
+constexpr int kMaxSmemOptin = 232448;  // 227 KB usable per CTA
+
+// ---- cp.async (LDGSTS) 16-byte copy, zero-fill when !pred --------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool pred) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    int src_bytes = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ---- activations ------------------------------------------------------------------------
+// ex2.approx-based; absolute error ~1e-7, far below the 1e-5 normalised parity bar
+// (tanh.approx.f32 would not be: 2^-11 relative).
+__device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanh_f(float v) {
+    // 1 - 2/(e^{2v}+1): exact limits at +-inf (e -> inf gives 1, e -> 0 gives -1)
+    return 1.0f - __fdividef(2.0f, __expf(2.0f * v) + 1.0f);
+}
+
+}  // namespace wg

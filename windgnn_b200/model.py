@@ -1,0 +1,70 @@
+"""Drop-in ``nn.Module`` mirrors of the reference model classes.
+
+Same constructor signatures, same parameter names (so the shipped ``wind_gnn_7.pth`` /
+``wind_gnn_34.pth`` state_dicts load with ``strict=True``), same ``forward(adj_matrix,
+attr_matrix)`` — but ``forward`` runs the fused sm_100a path through the C-ABI library.
+
+Reference: ``GraphConvLayer`` src/step5_gcn_layer_model.py:5-23,
+           ``GCN_GRU``        src/step6_gcn_gru_combined_model.py:6-27.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class GraphConvLayer(nn.Module):
+    """``relu((adj @ attr) @ weight + bias)`` — step5:13-23.  Init as step5:8-10."""
+
+    def __init__(self, input_dim, output_dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(input_dim, output_dim))
+        self.bias = nn.Parameter(torch.zeros(output_dim))
+
+    def forward(self, adj_matrix, attr_matrix):
+        return ops.gcn_layer(adj_matrix, attr_matrix, self.weight, self.bias)
+
+
+class GCN_GRU(nn.Module):
+    """conv1 -> conv2 -> flatten -> GRU, every hidden state returned (step6:13-27).
+
+    ``attr_matrix`` is ``[B, T, S, F_in]``.  The reference accepts ``B == 1`` only and
+    returns ``[T, H]`` (``squeeze(0)``, step6:26); that is reproduced, and ``B > 1`` returns
+    ``[B, T, H]`` (sequences are independent, ``h0 = 0`` each).
+
+    ``self.gru`` is a real ``nn.GRU`` used purely as the parameter container so that the
+    state_dict keys (``gru.weight_ih_l0`` ...) match the reference's.
+    """
+
+    def __init__(self, input_dim, hidden_dim, output_dim, gru_input, gru_hidden_dim):
+        super().__init__()
+        self.conv1 = GraphConvLayer(input_dim, hidden_dim)
+        self.conv2 = GraphConvLayer(hidden_dim, output_dim)
+        self.gru = nn.GRU(gru_input, gru_hidden_dim, batch_first=True)
+        self.chunk = 0  # sequences per internal pass; 0 = library default
+
+    def forward(self, adj_matrix, attr_matrix):
+        if attr_matrix.dim() != 4:
+            # the reference raises RuntimeError from view() for anything but [1, T, S, F] (step6:20)
+            raise RuntimeError(
+                f"attr_matrix must be [B, T, S, F_in], got {tuple(attr_matrix.shape)}"
+            )
+        out = ops.gcn_gru_forward(
+            adj_matrix, attr_matrix,
+            self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+            self.gru.weight_ih_l0, self.gru.weight_hh_l0, self.gru.bias_ih_l0, self.gru.bias_hh_l0,
+            self.chunk,
+        )
+        return out.squeeze(0)  # step6:26 — a no-op unless B == 1
+
+    @torch.no_grad()
+    def forward_host(self, adj_matrix, attr_host, out_host=None):
+        """Host-buffer end-to-end forward (H2D, compute, D2H overlapped chunk by chunk)."""
+        params = (
+            self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+            self.gru.weight_ih_l0, self.gru.weight_hh_l0, self.gru.bias_ih_l0, self.gru.bias_hh_l0,
+        )
+        return ops.gcn_gru_forward_host(adj_matrix, attr_host, [p.detach() for p in params], out_host, self.chunk)
