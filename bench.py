@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the WindGNN GCN-GRU forward hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one forward of the workload (BASELINE.json configs[1]: the shipped 34-station
+checkpoint, batch 4096 windows of 168 hours) — per GPU; with N > 1 (launched through
+``torch.distributed.run``) every rank runs the same per-GPU batch on its own device (weak scaling:
+the sequence batch is sharded, no collective on the data path).
+
+Prints ONE JSON line (rank 0).  ``value`` = sequences/s with the inputs resident in HBM; ``e2e`` =
+the same through the host-buffer entry point (pinned host input, H2D + compute + D2H inside the
+timed region); ``roofline`` = the dominant kernel (the input-projection FFMA GEMM) against the
+FP32 FFMA peak measured live on the same GPU; ``cpu_baseline`` = the oracle's torch-CPU port of
+the reference forward on this box's host cores.
+
+``--impl reference`` times that CPU port alone (the reference is pure Python/PyTorch and cannot
+travel to the GPU box; the port calls the same torch CPU kernels batch-generalised).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+METRIC = "gcn_gru_forward_sequences_per_s"
+UNIT = "sequences/s"
+
+# workload = BASELINE.json configs[1]
+S, T, F, B_PER_GPU = 34, 168, 13, 4096
+H, I = 3 * S, 13 * S
+FLOP_GCN = 2 * (2 * S * S * F + 2 * S * F * F)          # both layers, per (sequence, step)
+FLOP_IH = 2 * I * 3 * H
+FLOP_HH = 2 * H * 3 * H
+FLOP_PER_SEQ = T * (FLOP_GCN + FLOP_IH + FLOP_HH)        # 69,892,032
+BYTES_PER_SEQ = T * S * F * 4 + T * H * 4                # 365,568: input read once + output written once
+
+
+def load_workload():
+    sd = torch.load(os.path.join(GOLDEN, "wind_gnn_34.pth"), map_location="cpu", weights_only=True)
+    with open(os.path.join(GOLDEN, "coords.json")) as f:
+        c = json.load(f)
+    idx = [i for i, n in enumerate(c["names"]) if n != "Enchant 2 AGCM"]
+    latlon = np.array([[c["lat"][i], c["lon"][i]] for i in idx], dtype=np.float64)
+    return sd, latlon
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_seq_per_s(sd, adj32, n_seq: int, min_seconds: float, max_reps: int, seed: int = 0):
+    """The oracle's torch-CPU port (same library kernels as the reference, batch-generalised) on all
+    host threads.  Returns (sequences/s, threads, reps, seconds)."""
+    from oracle import gcn_gru_forward_torch
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand((n_seq, T, S, F), generator=g)
+    gcn_gru_forward_torch(adj32, x[: max(1, n_seq // 8)], sd)  # warm-up (thread pool, allocator)
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        gcn_gru_forward_torch(adj32, x, sd)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or reps >= max_reps:
+            break
+    return n_seq * reps / dt, threads, reps, dt
+
+
+def run_reference(args, rank: int):
+    """Reference arm: the CPU implementation of the path on the box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    sd, latlon = load_workload()
+    from oracle import dense_graph_f64
+
+    adj32 = torch.from_numpy(dense_graph_f64(latlon).astype(np.float32))
+    from oracle import gcn_gru_forward_torch
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n_seq = 512  # bounded sample of the 4096-sequence step
+    x = torch.rand((n_seq, T, S, F), generator=torch.Generator().manual_seed(0))
+    for _ in range(max(1, min(args.warmup, 2))):
+        gcn_gru_forward_torch(adj32, x[:64], sd)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gcn_gru_forward_torch(adj32, x, sd)
+    dt = time.perf_counter() - t0
+    value = n_seq * args.steps / dt
+    sample = f"{n_seq} of the {B_PER_GPU} sequences of each step, {args.steps} steps, torch CPU fp32, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "34-station GCN-GRU forward, wind_gnn_34.pth, T=168, CPU sample of B=4096",
+                   "S": S, "T": T, "batch_per_step": n_seq},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="sequences per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — windgnn_b200 has no CPU fallback")
+    import windgnn_b200
+    from windgnn_b200 import _lib
+
+    lib = _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: F811
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+    Bg = args.batch
+
+    sd, latlon = load_workload()
+    model = windgnn_b200.GCN_GRU(F, F, F, I, H)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    adj = windgnn_b200.build_graph_from_latlon(latlon, device=dev, dtype=torch.float32)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.rand((Bg, T, S, F), generator=gen, device=dev)  # 1.22 GB at B=4096: larger than the 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    with torch.no_grad():
+        for _ in range(warmup):
+            y = model(adj, x)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            barrier()
+            e0.record()
+            for _ in range(steps):
+                y = model(adj, x)
+            e1.record()
+            barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+    value = world * Bg * steps / (ms * 1e-3)
+    n_chunks = (Bg + 148 * 32 - 1) // (148 * 32)
+    launches_per_step = 1 + 3 * n_chunks  # pack + (gcn, inproj, recur) per internal chunk
+
+    # ---------------- per-kernel timing for the roofline (rank 0's GPU, same stream) -------------
+    dims = (T, S, F, F, F, H)
+    stage_ms = {}
+    if rank == 0:
+        Bc = min(Bg, 148 * 32)
+        nbytes = lib.wg_gcn_gru_workspace_bytes(Bc, *dims, Bc)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty((Bc, T, H), device=dev)
+        p = [t.detach().contiguous() for t in (
+            model.conv1.weight, model.conv1.bias, model.conv2.weight, model.conv2.bias,
+            model.gru.weight_ih_l0, model.gru.weight_hh_l0, model.gru.bias_ih_l0, model.gru.bias_hh_l0)]
+        st = torch.cuda.current_stream(dev).cuda_stream
+        xs = x[:Bc]
+        calls = {
+            "pack": lambda: lib.wg_stage_pack_f32(*(t.data_ptr() for t in p[4:]), *dims, Bc, ws.data_ptr(), nbytes, local_rank, st),
+            "gcn": lambda: lib.wg_stage_gcn_f32(adj.data_ptr(), xs.data_ptr(), *(t.data_ptr() for t in p[:4]), Bc, *dims, Bc, ws.data_ptr(), nbytes, local_rank, st),
+            "inproj": lambda: lib.wg_stage_inproj_f32(Bc, *dims, Bc, ws.data_ptr(), nbytes, local_rank, st),
+            "recur": lambda: lib.wg_stage_recur_f32(out.data_ptr(), Bc, *dims, Bc, ws.data_ptr(), nbytes, local_rank, st),
+        }
+        for name in ("pack", "gcn", "inproj", "recur"):
+            for _ in range(3):
+                _lib.check(calls[name]())
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(5, min(steps, 20))
+            a.record()
+            for _ in range(reps):
+                _lib.check(calls[name]())
+            b.record()
+            torch.cuda.synchronize(dev)
+            stage_ms[name] = a.elapsed_time(b) / reps
+        ffma_peak = lib.wg_measure_ffma_tflops(local_rank, 10)
+        del ws, out
+    barrier()
+
+    # ---------------- end-to-end through the host-buffer entry point ----------------
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty((Bg, T, S, F), dtype=torch.float32, pin_memory=True)
+        xh.copy_(x)
+        oh = torch.empty((Bg, T, H), dtype=torch.float32, pin_memory=True)
+        model.chunk = 512  # pipeline granularity: H2D / compute / D2H of consecutive chunks overlap
+        e2e_steps = max(3, min(steps, 10))
+        with torch.no_grad():
+            for _ in range(2):
+                model.forward_host(adj, xh, oh)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                model.forward_host(adj, xh, oh)  # blocks until `oh` is complete
+            torch.cuda.synchronize(dev)
+            dt = max_over_ranks(time.perf_counter() - t0)
+        model.chunk = 0
+        e2e = {"value": world * Bg * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": Bg * T * S * F * 4, "d2h_bytes_per_step": Bg * T * H * 4,
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "pipeline_chunk": 512}
+        del xh, oh
+    barrier()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+        Bc = min(Bg, 148 * 32)
+        rows = Bc * T
+        inproj_flops = FLOP_IH * rows
+        inproj_tflops = inproj_flops / (stage_ms["inproj"] * 1e-3) / 1e12
+        nominal_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+        path_tflops = FLOP_PER_SEQ * Bg * steps / (ms * 1e-3) / 1e12  # per GPU
+        hbm_gbs = BYTES_PER_SEQ * Bg * steps / (ms * 1e-3) / 1e9     # per GPU, algorithmic
+        roofline = {
+            "bound": "fp32", "kernel": "inproj_kernel (GRU input projection, FFMA GEMM)",
+            "achieved": inproj_tflops, "peak": ffma_peak, "unit": "TFLOP/s", "frac": inproj_tflops / ffma_peak,
+            "peak_source": "FFMA microbenchmark measured live on this GPU (wg_measure_ffma_tflops)",
+            "peak_nominal": nominal_peak, "traffic": None,
+            "algorithmic_flops_per_launch": inproj_flops,
+            "kernel_ms": stage_ms,
+            "path": {"achieved": path_tflops, "frac_fp32": path_tflops / ffma_peak,
+                     "hbm_gbs": hbm_gbs, "hbm_peak": hbm_peak, "hbm_peak_source": hbm_src,
+                     "frac_hbm": hbm_gbs / hbm_peak, "flop_per_seq": FLOP_PER_SEQ, "bytes_per_seq": BYTES_PER_SEQ},
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            adj_cpu = adj.cpu()
+            v, threads, reps, secs = cpu_port_seq_per_s(sd, adj_cpu, n_seq=1024, min_seconds=10.0, max_reps=20)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{reps} x 1024 sequences of the same workload in {secs:.1f} s, torch CPU fp32"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "34-station GCN-GRU forward (wind_gnn_34.pth), T=168, batch 4096 per GPU "
+                                   "(BASELINE.json configs[1])", "S": S, "T": T, "batch_per_gpu": Bg,
+                       "global_batch": Bg * world, "parallelism": f"sequence-sharded x{world}, no collective",
+                       "l2_policy": "inputs (1.22 GB per step) larger than L2",
+                       "station_sequence_predictions_per_s": value * S},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * steps,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
