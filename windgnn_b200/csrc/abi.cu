@@ -89,7 +89,8 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     p.off_wht = o;  o = align_up(o + (size_t)p.KP * p.NPR * 4);
     p.off_bhn = o;  o = align_up(o + (size_t)p.KP * 4);
     const size_t rows = (size_t)p.chunk * T;
-    p.off_u = o;    o = align_up(o + rows * p.IP * 4);
+    const size_t rows_tiled = (rows + wg::kUTileRows - 1) / wg::kUTileRows * wg::kUTileRows;
+    p.off_u = o;    o = align_up(o + rows_tiled * p.IP * 4);  // K-major 128-row tiles
     p.off_gi = o;   o = align_up(o + rows * p.GP * 4);
     p.total = o;
     return WG_OK;
@@ -121,7 +122,10 @@ __global__ void pack_params_kernel(const float* __restrict__ w_ih, const float* 
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (long long e = t0; e < n_wp; e += stride) {
-        const int n = (int)(e / IP), k = (int)(e % IP);
+        // destination layout [n / 64][k][n % 64] (K-major 64-column tiles, see inproj.cuh)
+        const int nl = (int)(e % wg::kIpBN);
+        const long long r = e / wg::kIpBN;
+        const int k = (int)(r % IP), n = (int)(r / IP) * wg::kIpBN + nl;
         wp[e] = (n < G && k < I) ? w_ih[(size_t)n * I + k] : 0.0f;
     }
     for (long long e = t0; e < n_wht; e += stride) {
@@ -139,7 +143,7 @@ __global__ void pack_params_kernel(const float* __restrict__ w_ih, const float* 
 // ---------------------------------------------------------------------------------------------
 // stage launchers
 // ---------------------------------------------------------------------------------------------
-template <int FP, int SG, bool EXACT, int LAYERS>
+template <int FP, int SG, int LAYERS, bool TILED>
 int launch_gcn_t(const float* X, const float* adj, const float* W1, const float* b1, const float* W2,
                  const float* b2, float* out, long long R, int S, int Fi, int Fh, int Fo, int ldo,
                  cudaStream_t st) {
@@ -147,19 +151,19 @@ int launch_gcn_t(const float* X, const float* adj, const float* W1, const float*
     if (NSG > wg::kGcnThreads)
         return fail(WG_ERR_UNSUPPORTED, "S=%d too large for the dense GCN kernel", S);
     int RB = wg::kGcnThreads / NSG;
-    size_t smem = wg::gcn_smem_floats<FP, SG>(S, Fi, Fh, Fo, RB, LAYERS) * 4;
+    size_t smem = wg::gcn_smem_floats<FP, SG>(S, RB) * 4;
+    // aim for >= 3 resident CTAs per SM when the slabs allow it
+    while (smem > (size_t)wg::kMaxSmemOptin / 3 && RB > 8) {
+        RB = RB - (RB + 7) / 8;
+        smem = wg::gcn_smem_floats<FP, SG>(S, RB) * 4;
+    }
     while (smem > (size_t)wg::kMaxSmemOptin && RB > 1) {
         RB = RB / 2;
-        smem = wg::gcn_smem_floats<FP, SG>(S, Fi, Fh, Fo, RB, LAYERS) * 4;
-    }
-    // keep >= 2 CTAs per SM resident when the slabs allow it
-    while (smem > (size_t)wg::kMaxSmemOptin / 2 && RB > 8) {
-        RB = RB - RB / 4;
-        smem = wg::gcn_smem_floats<FP, SG>(S, Fi, Fh, Fo, RB, LAYERS) * 4;
+        smem = wg::gcn_smem_floats<FP, SG>(S, RB) * 4;
     }
     if (smem > (size_t)wg::kMaxSmemOptin)
         return fail(WG_ERR_UNSUPPORTED, "dense GCN needs %zu B of shared memory (S=%d); use the sparse path", smem, S);
-    auto kern = wg::gcn_kernel<FP, SG, EXACT, LAYERS>;
+    auto kern = wg::gcn_kernel<FP, SG, LAYERS, TILED>;
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     WG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wg::kGcnThreads, smem));
@@ -173,15 +177,22 @@ int launch_gcn_t(const float* X, const float* adj, const float* W1, const float*
     return WG_OK;
 }
 
-template <int LAYERS>
+// stations per thread: 7 or 4, whichever pads S less (ties: 7)
+int pick_sg(int S) {
+    return wg::ceil_div(S, 7) * 7 <= wg::ceil_div(S, 4) * 4 ? 7 : 4;
+}
+
+template <int LAYERS, bool TILED>
 int launch_gcn(const float* X, const float* adj, const float* W1, const float* b1, const float* W2,
                const float* b2, float* out, long long R, int S, int Fi, int Fh, int Fo, int ldo,
                cudaStream_t st) {
     const int fmax = Fi > Fh ? (Fi > Fo ? Fi : Fo) : (Fh > Fo ? Fh : Fo);
-    if (Fi == 13 && Fh == 13 && Fo == 13)
-        return launch_gcn_t<13, 7, true, LAYERS>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, st);
-    if (fmax <= 16)
-        return launch_gcn_t<16, 4, false, LAYERS>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, st);
+#define WG_GCN(FP, SG) launch_gcn_t<FP, SG, LAYERS, TILED>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, st)
+    if (fmax <= 13) {
+        return pick_sg(S) == 7 ? WG_GCN(13, 7) : WG_GCN(13, 4);
+    }
+    if (fmax <= 16) return WG_GCN(16, 4);
+#undef WG_GCN
     return fail(WG_ERR_UNSUPPORTED, "GCN feature width %d > 16 is not built into the dense kernel", fmax);
 }
 
@@ -195,14 +206,14 @@ int launch_inproj(const Plan& p, void* ws, long long rows, cudaStream_t st) {
                                  wg::kIpSmemBytes));
     wg::inproj_kernel<<<(unsigned)grid, wg::kIpThreads, wg::kIpSmemBytes, st>>>(
         ws_ptr<float>(ws, p.off_u), ws_ptr<float>(ws, p.off_wp), ws_ptr<float>(ws, p.off_bias),
-        ws_ptr<float>(ws, p.off_gi), rows, p.G, p.IP, p.GP, n_tiles);
+        ws_ptr<float>(ws, p.off_gi), rows, p.IP, p.GP, n_tiles);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
 
 template <int NW, bool WS>
 int launch_recur_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
-    const size_t smem = wg::recur_smem_floats(p.KP, p.NPR, WS) * 4;
+    const size_t smem = wg::recur_smem_floats(p.KP, p.NPR, p.GP, WS) * 4;
     auto kern = wg::gru_recur_kernel<NW, WS>;
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (Bc + wg::kRcBT - 1) / wg::kRcBT;
@@ -232,9 +243,9 @@ int launch_recur_ws(const Plan& p, void* ws, float* out, long long Bc, cudaStrea
 }
 
 int launch_recur(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
-    const size_t smem_ws = wg::recur_smem_floats(p.KP, p.NPR, true) * 4;
+    const size_t smem_ws = wg::recur_smem_floats(p.KP, p.NPR, p.GP, true) * 4;
     if (smem_ws <= (size_t)wg::kMaxSmemOptin) return launch_recur_ws<true>(p, ws, out, Bc, st);
-    const size_t smem_nows = wg::recur_smem_floats(p.KP, p.NPR, false) * 4;
+    const size_t smem_nows = wg::recur_smem_floats(p.KP, p.NPR, p.GP, false) * 4;
     if (smem_nows <= (size_t)wg::kMaxSmemOptin) return launch_recur_ws<false>(p, ws, out, Bc, st);
     return fail(WG_ERR_UNSUPPORTED, "GRU hidden size %d: state does not fit shared memory", p.H);
 }
@@ -252,8 +263,8 @@ int launch_pack(const Plan& p, void* ws, const float* w_ih, const float* w_hh, c
 int run_chunk(const Plan& p, void* ws, const float* adj, const float* x, const float* w1, const float* b1,
               const float* w2, const float* b2, float* out, long long Bc, cudaStream_t st) {
     const long long rows = Bc * p.T;
-    int rc = launch_gcn<2>(x, adj, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_u), rows, p.S, p.Fi, p.Fh, p.Fo,
-                           p.IP, st);
+    int rc = launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_u), rows, p.S, p.Fi, p.Fh,
+                                 p.Fo, p.IP, st);
     if (rc) return rc;
     rc = launch_inproj(p, ws, rows, st);
     if (rc) return rc;
@@ -322,8 +333,8 @@ int wg_stage_gcn_f32(const float* adj, const float* x, const float* w1, const fl
     if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
     DeviceGuard g(device);
     WG_CUDA(g.err);
-    return launch_gcn<2>(x, adj, w1, b1, w2, b2, ws_ptr<float>(workspace, p.off_u), (long long)Bc * T, S,
-                         F_in, F_hid, F_out, p.IP, static_cast<cudaStream_t>(stream));
+    return launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(workspace, p.off_u), (long long)Bc * T, S,
+                               F_in, F_hid, F_out, p.IP, static_cast<cudaStream_t>(stream));
 }
 
 int wg_stage_inproj_f32(int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H, int64_t chunk,
@@ -494,8 +505,8 @@ int wg_gcn_layer_f32(const float* adj, const float* attr, const float* weight, c
     DeviceGuard g(device);
     WG_CUDA(g.err);
     // single layer: "hidden" plays the role of the output width
-    return launch_gcn<1>(attr, adj, weight, bias, nullptr, nullptr, out, R, S, F_in, F_out, F_out,
-                         S * F_out, static_cast<cudaStream_t>(stream));
+    return launch_gcn<1, false>(attr, adj, weight, bias, nullptr, nullptr, out, R, S, F_in, F_out, F_out,
+                                S * F_out, static_cast<cudaStream_t>(stream));
 }
 
 double wg_measure_ffma_tflops(int device, int iters) {

@@ -2,16 +2,20 @@
 //
 // Reference: GraphConvLayer.forward, src/step5_gcn_layer_model.py:13-23 (matmul order :15,:18,
 // ReLU :21); chained twice by GCN_GRU.forward, src/step6_gcn_gru_combined_model.py:17,20, whose
-// `.view(1, T, S*13)` (:20) is the flat index s*F_out + f used for the output rows here.
+// `.view(1, T, S*13)` (:20) is the flat index s*F_out + f used for the output columns here.
 //
 // Work decomposition (dense A_hat, S small enough for A_hat^T to sit in shared memory):
-//   * a CTA owns RB consecutive rows (a row = one (sequence, timestep) pair = an [S, F] slab);
-//   * a thread owns SG consecutive stations of one row: it keeps the SG x F aggregate
-//     in registers, runs the S-long aggregation as register FFMAs (A_hat^T column group by
-//     LDS.128, the S x F input slab by warp-broadcast LDS), then applies the F x F transform,
-//     bias and ReLU from registers and writes the result slab to shared memory;
-//   * layer 2 reads layer 1's slab from shared memory; only the final slab goes to HBM,
-//     zero-padded to `ldo` columns so the input-projection GEMM needs no K-edge handling.
+//   * a CTA owns RB consecutive rows (a row = one (sequence, timestep) pair = an [S, F] slab)
+//     held in ONE shared-memory buffer, features padded to 16 floats per station so a station's
+//     feature vector is four LDS.128; both layers run in place (aggregate -> barrier -> write);
+//   * a thread owns SG consecutive stations of one row and keeps their aggregate in registers
+//     as FEATURE pairs: the S-long aggregation is packed FP32 FMAs (FFMA2, sm_100a: two fp32
+//     FMAs per instruction) acc2[s][fp] += (A[s][s'], A[s][s']) * (x[s'][2fp], x[s'][2fp+1]),
+//     the feature pairs coming straight out of the slab's LDS.128; the F x F transform is FFMA2
+//     too (pairs along the contracted feature index, two partial sums added at the end);
+//   * only the final slab goes to HBM: either row-major (single-layer op) or, for the fused
+//     path, in the K-major 128-row tiles the input-projection GEMM copies with one bulk
+//     async copy per stage (inproj.cuh), zero-padded to `ldo` columns.
 #pragma once
 
 #include "wg_common.cuh"
@@ -19,128 +23,148 @@
 namespace wg {
 
 constexpr int kGcnThreads = 128;
+#ifndef WG_GCN_MINB
+#define WG_GCN_MINB 3  // resident CTAs per SM the register budget is planned for (<= 168 regs)
+#endif
+constexpr int kGcnFS = 16;   // floats per station in the shared slab
+constexpr int kUTileRows = 128;  // rows per K-major tile of the tiled output (= inproj BM)
 
-// Floats of dynamic shared memory the kernel needs.
+__host__ __device__ inline int gcn_row_stride(int S) { return S * kGcnFS + 4; }
+
 template <int FP, int SG>
-__host__ __device__ inline size_t gcn_smem_floats(int S, int Fi, int Fh, int Fo, int RB, int layers) {
-    constexpr int SGS = (SG + 3) & ~3;
-    constexpr int FPAD = (FP + 3) & ~3;
+__host__ __device__ inline size_t gcn_smem_floats(int S, int RB) {
     const int NSG = ceil_div(S, SG);
-    const int fmaxA = layers == 2 ? (Fi > Fo ? Fi : Fo) : Fi;
     size_t n = 0;
-    n += (size_t)S * NSG * SGS;             // adjT
-    n += 2 * (size_t)FPAD * FPAD;           // w1t, w2t ([fo][FPAD], fo < FPAD)
-    n += 2 * (size_t)FPAD;                  // b1, b2
-    n += (size_t)round_up(RB * S * fmaxA, 4);  // bufA
-    n += (size_t)round_up(RB * S * (layers == 2 ? Fh : Fo), 4);  // bufB
+    n += (size_t)S * NSG * 8;           // adjT: [S][NSG][8] (SG <= 8 stations per group)
+    n += 2 * (size_t)kGcnFS * kGcnFS;   // w1p, w2p: [fp][fo][2] feature-pair weights
+    n += 2 * (size_t)kGcnFS;            // b1, b2
+    n += (size_t)RB * gcn_row_stride(S);
     return n;
 }
 
-// One GCN layer on the CTA's row block, shared memory -> shared memory.
-//   in  [rows][S*Fi], outp [rows][S*Fo]; adjT [S][NSG*SGS] with adjT[sp][q*SGS+i] = A_hat[q*SG+i][sp]
-//   (zero where the station index is out of range); Wt [Fo][FPAD] (f contiguous, zero padded).
-template <int FP, int SG, bool EXACT>
-__device__ __forceinline__ void gcn_layer_smem(const float* __restrict__ in, float* __restrict__ outp,
-                                               const float* __restrict__ adjT,
-                                               const float* __restrict__ Wt,
-                                               const float* __restrict__ bias, int S, int Fi, int Fo,
-                                               int NSG, int row_local, int q) {
-    constexpr int SGS = (SG + 3) & ~3;
-    constexpr int FPAD = (FP + 3) & ~3;
-    float acc[SG][FP];
-#pragma unroll
-    for (int i = 0; i < SG; ++i)
-#pragma unroll
-        for (int f = 0; f < FP; ++f) acc[i][f] = 0.0f;
-
-    const float* xrow = in + (size_t)row_local * S * Fi;
-    const float* arow = adjT + q * SGS;
-    const int astride = NSG * SGS;
-#pragma unroll 2
-    for (int sp = 0; sp < S; ++sp) {
-        float a[SGS];
-#pragma unroll
-        for (int v = 0; v < SGS / 4; ++v) {
-            const float4 t = *reinterpret_cast<const float4*>(arow + (size_t)sp * astride + 4 * v);
-            a[4 * v + 0] = t.x;
-            a[4 * v + 1] = t.y;
-            a[4 * v + 2] = t.z;
-            a[4 * v + 3] = t.w;
-        }
-        float x[FP];
-#pragma unroll
-        for (int f = 0; f < FP; ++f) x[f] = (EXACT || f < Fi) ? xrow[sp * Fi + f] : 0.0f;
+// One GCN layer on the CTA's row block, in place in shared memory.
+//   buf   [rows][S][16] (+4 pad per row): features of the layer input, overwritten by its output
+//   adjT  [S][NSG][8]: adjT[sp][q][i] = A_hat[q*SG+i][sp] (zero where out of range)
+//   Wp    [8][16][2]: Wp[fp][fo] = (W[2fp][fo], W[2fp+1][fo]) (zero padded)
+// Packed math: the aggregate is kept as FEATURE pairs, acc2[s][fp] = (agg[s][2fp], agg[s][2fp+1]):
+//   aggregation  acc2[s][fp] += (A[s][s'], A[s][s']) * (x[s'][2fp], x[s'][2fp+1])   (x pairs come
+//                straight out of the LDS.128 of the slab, one broadcast MOV per station)
+//   transform    o2[s][fo]  += acc2[s][fp] * (W[2fp][fo], W[2fp+1][fo]);  out = o2.x + o2.y + b
+template <int FP, int SG>
+__device__ __noinline__ void gcn_layer_inplace(float* __restrict__ buf, const float* __restrict__ adjT,
+                                                  const float* __restrict__ Wp,
+                                                  const float* __restrict__ bias, int S, int Fo, int NSG,
+                                                  int row_local, int q, bool active) {
+    constexpr int FPP = (FP + 1) / 2;  // feature pairs
+    float2 acc[SG][FPP];
+    if (active) {
 #pragma unroll
         for (int i = 0; i < SG; ++i)
 #pragma unroll
-            for (int f = 0; f < FP; ++f) acc[i][f] = fmaf(a[i], x[f], acc[i][f]);
-    }
-
-    float* orow = outp + (size_t)row_local * S * Fo;
-    for (int fo = 0; fo < Fo; ++fo) {
-        float w[FPAD];
+            for (int fp = 0; fp < FPP; ++fp) acc[i][fp] = make_float2(0.0f, 0.0f);
+        const float* xrow = buf + (size_t)row_local * gcn_row_stride(S);
+        const float* arow = adjT + q * 8;
+        const int astride = NSG * 8;
+#pragma unroll 1
+        for (int sp = 0; sp < S; ++sp) {
+            float a[8];
+            {
+                const float4 t0 = *reinterpret_cast<const float4*>(arow + (size_t)sp * astride);
+                a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w;
+                if (SG > 4) {
+                    const float4 t1 = *reinterpret_cast<const float4*>(arow + (size_t)sp * astride + 4);
+                    a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+                }
+            }
+            float2 xp[8];
 #pragma unroll
-        for (int v = 0; v < FPAD / 4; ++v) {
-            const float4 t = *reinterpret_cast<const float4*>(Wt + fo * FPAD + 4 * v);
-            w[4 * v + 0] = t.x;
-            w[4 * v + 1] = t.y;
-            w[4 * v + 2] = t.z;
-            w[4 * v + 3] = t.w;
+            for (int v = 0; v < (FPP + 1) / 2; ++v) {
+                const float4 t = *reinterpret_cast<const float4*>(xrow + sp * kGcnFS + 4 * v);
+                xp[2 * v] = make_float2(t.x, t.y);
+                xp[2 * v + 1] = make_float2(t.z, t.w);
+            }
+#pragma unroll
+            for (int i = 0; i < SG; ++i) {
+                const float2 aa = make_float2(a[i], a[i]);
+#pragma unroll
+                for (int fp = 0; fp < FPP; ++fp) acc[i][fp] = __ffma2_rn(aa, xp[fp], acc[i][fp]);
+            }
         }
-        const float b = bias[fo];
+    }
+    __syncthreads();  // every thread has finished reading the input slab
+    if (active) {
+        float* orow = buf + (size_t)row_local * gcn_row_stride(S) + q * SG * kGcnFS;
+#pragma unroll 1
+        for (int fo0 = 0; fo0 < Fo; fo0 += 2) {
+            float2 o[SG][2];
 #pragma unroll
-        for (int i = 0; i < SG; ++i) {
-            const int s = q * SG + i;
-            float v = 0.0f;
+            for (int i = 0; i < SG; ++i) o[i][0] = o[i][1] = make_float2(0.0f, 0.0f);
 #pragma unroll
-            for (int f = 0; f < FP; ++f) v = fmaf(acc[i][f], w[f], v);
-            v += b;
-            v = v < 0.0f ? 0.0f : v;  // ReLU; NaN propagates like torch.relu
-            if (s < S) orow[s * Fo + fo] = v;
+            for (int fp = 0; fp < FPP; ++fp) {
+                const float4 w = *reinterpret_cast<const float4*>(Wp + (fp * kGcnFS + fo0) * 2);
+#pragma unroll
+                for (int i = 0; i < SG; ++i) {
+                    o[i][0] = __ffma2_rn(acc[i][fp], make_float2(w.x, w.y), o[i][0]);
+                    o[i][1] = __ffma2_rn(acc[i][fp], make_float2(w.z, w.w), o[i][1]);
+                }
+            }
+            const float2 bb = *reinterpret_cast<const float2*>(bias + fo0);
+#pragma unroll
+            for (int i = 0; i < SG; ++i) {
+                float u0 = (o[i][0].x + o[i][0].y) + bb.x;
+                float u1 = (o[i][1].x + o[i][1].y) + bb.y;
+                u0 = u0 < 0.0f ? 0.0f : u0;  // ReLU; NaN propagates like torch.relu
+                u1 = u1 < 0.0f ? 0.0f : u1;
+                // an odd Fo writes one extra column: relu(0 + 0) = 0 into the station's pad lanes
+                if (q * SG + i < S) *reinterpret_cast<float2*>(orow + i * kGcnFS + fo0) = make_float2(u0, u1);
+            }
         }
     }
+    __syncthreads();
 }
 
-// LAYERS == 2: out[r][c] (ld = ldo, c < ldo) = flatten(relu-GCN2(relu-GCN1(x[r]))) zero padded.
-// LAYERS == 1: out[r][c] = flatten(relu-GCN1(x[r])), W2/b2 unused, Fh := Fo.
-template <int FP, int SG, bool EXACT, int LAYERS>
-__global__ void __launch_bounds__(kGcnThreads)
+// LAYERS == 2: GCN2(GCN1(x)) ; LAYERS == 1: GCN1(x) (W2/b2 unused, pass Fh = Fo = output width).
+// TILED: out is [ceil(R/128)][ldo][128] (K-major row tiles, zero padded columns) else [R][ldo]
+// row-major with ldo == S * F_last.
+template <int FP, int SG, int LAYERS, bool TILED>
+__global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
     gcn_kernel(const float* __restrict__ X, const float* __restrict__ adj, const float* __restrict__ W1,
                const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
                float* __restrict__ out, long long R, int S, int Fi, int Fh, int Fo, int ldo, int RB) {
-    constexpr int SGS = (SG + 3) & ~3;
-    constexpr int FPAD = (FP + 3) & ~3;
     extern __shared__ __align__(16) float smem[];
     const int NSG = ceil_div(S, SG);
     const int tid = threadIdx.x;
-    const int Flast = LAYERS == 2 ? Fo : Fh;  // features of the final slab
-    const int fmaxA = LAYERS == 2 ? (Fi > Fo ? Fi : Fo) : Fi;
+    const int Flast = LAYERS == 2 ? Fo : Fh;
+    const int RS = gcn_row_stride(S);
 
     float* adjT = smem;
-    float* w1t = adjT + (size_t)S * NSG * SGS;
-    float* w2t = w1t + FPAD * FPAD;
-    float* b1s = w2t + FPAD * FPAD;
-    float* b2s = b1s + FPAD;
-    float* bufA = b2s + FPAD;
-    float* bufB = bufA + round_up(RB * S * fmaxA, 4);
+    float* w1d = adjT + (size_t)S * NSG * 8;
+    float* w2d = w1d + kGcnFS * kGcnFS;
+    float* b1s = w2d + kGcnFS * kGcnFS;
+    float* b2s = b1s + kGcnFS;
+    float* buf = b2s + kGcnFS;
 
     // ---- stage the (tiny) graph and layer parameters once per CTA ----
-    for (int e = tid; e < S * NSG * SGS; e += kGcnThreads) {
-        const int sp = e / (NSG * SGS);
-        const int c = e % (NSG * SGS);
-        const int qq = c / SGS, i = c % SGS;
+    for (int e = tid; e < S * NSG * 8; e += kGcnThreads) {
+        const int sp = e / (NSG * 8);
+        const int c = e % (NSG * 8);
+        const int qq = c >> 3, i = c & 7;
         const int s = qq * SG + i;
         adjT[e] = (i < SG && s < S) ? adj[(size_t)s * S + sp] : 0.0f;
     }
-    for (int e = tid; e < FPAD * FPAD; e += kGcnThreads) {
-        const int fo = e / FPAD, f = e % FPAD;
-        w1t[e] = (fo < Fh && f < Fi) ? W1[f * Fh + fo] : 0.0f;
-        if (LAYERS == 2) w2t[e] = (fo < Fo && f < Fh) ? W2[f * Fo + fo] : 0.0f;
+    for (int e = tid; e < kGcnFS * kGcnFS; e += kGcnThreads) {
+        // e = (fp * 16 + fo) * 2 + h  ->  W[2 fp + h][fo]
+        const int h = e & 1, fo = (e >> 1) % kGcnFS, fp = (e >> 1) / kGcnFS;
+        const int f = 2 * fp + h;
+        w1d[e] = (f < Fi && fo < Fh) ? W1[f * Fh + fo] : 0.0f;
+        w2d[e] = (LAYERS == 2 && f < Fh && fo < Fo) ? W2[f * Fo + fo] : 0.0f;
     }
-    for (int e = tid; e < FPAD; e += kGcnThreads) {
+    for (int e = tid; e < kGcnFS; e += kGcnThreads) {
         b1s[e] = e < Fh ? b1[e] : 0.0f;
-        if (LAYERS == 2) b2s[e] = e < Fo ? b2[e] : 0.0f;
+        b2s[e] = (LAYERS == 2 && e < Fo) ? b2[e] : 0.0f;
     }
+    // the slab's pad lanes (f >= F) must hold finite values: they meet zero weights
+    for (int e = tid; e < RB * RS; e += kGcnThreads) buf[e] = 0.0f;
     __syncthreads();
 
     const int row_local = tid / NSG;
@@ -148,46 +172,56 @@ __global__ void __launch_bounds__(kGcnThreads)
     const long long nblocks = (R + RB - 1) / RB;
     const int in_cols = S * Fi;
     const int out_cols = S * Flast;
+    // per-thread stepping of (row, station, feature) by kGcnThreads elements of the input block
+    const int step_rs = kGcnThreads / Fi, step_f = kGcnThreads % Fi;
 
     for (long long rb = blockIdx.x; rb < nblocks; rb += gridDim.x) {
         const long long r0 = rb * RB;
         const int nrows = (int)((R - r0) < RB ? (R - r0) : RB);
-        // ---- coalesced copy of the row block (contiguous in HBM) ----
-        const float* src = X + (size_t)r0 * in_cols;
-        const int n_in = nrows * in_cols;
-        for (int e = tid; e < n_in; e += kGcnThreads) bufA[e] = __ldg(src + e);
+        // ---- coalesced copy of the row block (contiguous in HBM) into the padded slab ----
+        {
+            const float* src = X + (size_t)r0 * in_cols;
+            const int n_in = nrows * in_cols;
+            int f = tid % Fi, rs = tid / Fi;          // rs = row * S + station
+            int row = rs / S, st = rs - row * S;
+            for (int e = tid; e < n_in; e += kGcnThreads) {
+                buf[row * RS + st * kGcnFS + f] = __ldg(src + e);
+                f += step_f;
+                st += step_rs;
+                if (f >= Fi) { f -= Fi; ++st; }
+                while (st >= S) { st -= S; ++row; }
+            }
+        }
         __syncthreads();
 
         const bool active = row_local < nrows;
-        if (active) gcn_layer_smem<FP, SG, EXACT>(bufA, bufB, adjT, w1t, b1s, S, Fi, Fh, NSG, row_local, q);
-        __syncthreads();
-        const float* fin = bufB;
-        if (LAYERS == 2) {
-            if (active) gcn_layer_smem<FP, SG, EXACT>(bufB, bufA, adjT, w2t, b2s, S, Fh, Fo, NSG, row_local, q);
-            __syncthreads();
-            fin = bufA;
-        }
-        // ---- coalesced store of the final slab, zero padded to ldo columns ----
-        float* dst = out + (size_t)r0 * ldo;
-        if ((ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-            const int ld4 = ldo >> 2;
-            const int n4 = nrows * ld4;
-            for (int e = tid; e < n4; e += kGcnThreads) {
-                const int row = e / ld4;
-                const int c = (e % ld4) * 4;
-                const float* p = fin + row * out_cols;
-                float4 v;
-                v.x = (c + 0 < out_cols) ? p[c + 0] : 0.0f;
-                v.y = (c + 1 < out_cols) ? p[c + 1] : 0.0f;
-                v.z = (c + 2 < out_cols) ? p[c + 2] : 0.0f;
-                v.w = (c + 3 < out_cols) ? p[c + 3] : 0.0f;
-                *reinterpret_cast<float4*>(dst + (size_t)row * ldo + c) = v;
+        gcn_layer_inplace<FP, SG>(buf, adjT, w1d, b1s, S, Fh, NSG, row_local, q, active);
+        if (LAYERS == 2) gcn_layer_inplace<FP, SG>(buf, adjT, w2d, b2s, S, Fo, NSG, row_local, q, active);
+
+        // ---- store the final slab ----
+        if (TILED) {
+            // out[(r / 128)][c][r % 128]; consecutive threads -> consecutive rows of one column
+            const int n_out = nrows * ldo;
+            int rl = tid % nrows, c = tid / nrows;
+            const int step_c = kGcnThreads / nrows, step_r = kGcnThreads % nrows;
+            int st = c / Flast, f = c - st * Flast;
+            for (int e = tid; e < n_out; e += kGcnThreads) {
+                const long long r = r0 + rl;
+                const float v = c < out_cols ? buf[rl * RS + st * kGcnFS + f] : 0.0f;
+                out[((size_t)(r / kUTileRows) * ldo + c) * kUTileRows + (r % kUTileRows)] = v;
+                rl += step_r;
+                c += step_c;
+                if (rl >= nrows) { rl -= nrows; ++c; }
+                st = c / Flast;
+                f = c - st * Flast;
             }
         } else {
+            float* dst = out + (size_t)r0 * ldo;
             const int n_out = nrows * ldo;
             for (int e = tid; e < n_out; e += kGcnThreads) {
-                const int row = e / ldo, c = e % ldo;
-                dst[e] = c < out_cols ? fin[row * out_cols + c] : 0.0f;
+                const int row = e / ldo, c = e - row * ldo;
+                const int st = c / Flast, f = c - st * Flast;
+                dst[e] = buf[row * RS + st * kGcnFS + f];
             }
         }
         __syncthreads();

@@ -9,13 +9,16 @@
 //
 // A CTA owns 32 sequences for all T steps.  W_hh^T ([k][n], zero padded to KP x NP) lives in
 // shared memory for the whole kernel, the hidden state of the 32 sequences too; nothing but gi
-// (read) and h (written) touches HBM inside the time loop.  Each step has two phases:
-//   GEMM  : gs[b][n] = sum_k hs[b][k] * Ws[k][n].  Warp tile 16 sequences x 32 gate columns,
-//           thread tile 4 x 4, all operands by LDS.128 (hs rows padded so the four row
-//           offsets of a warp fall in distinct bank groups; Ws rows are read 128 B contiguous).
+// (read) and h (written) touches HBM inside the time loop.  Per step:
+//   GEMM  : acc[b][n] = sum_k h[b][k] * W[k][n] on the FMA pipe with packed FFMA2 (pairs along n;
+//           the hidden state is kept DUPLICATED in shared memory, (h, h), so both FFMA2 operands
+//           are plain LDS.128 register pairs).  Warp tile 16 sequences x 32 gate columns, thread
+//           tile 4 x 4, 20 warps at S = 34 (5 per scheduler).
+//   merge : each thread adds its accumulators onto the gi tile that IT prefetched with cp.async
+//           during the GEMM (16-byte chunks, no barrier needed: a thread only waits for its own
+//           copies); the n-gate part of gh is kept apart because r multiplies it.
 //   gates : one (sequence, hidden unit) item per thread-slot, lanes along the hidden index so
-//           the gi loads / h stores are coalesced; gi for step t+1 is prefetched into registers
-//           while step t's gates and step t+1's GEMM run.
+//           the h stores to HBM are coalesced.
 #pragma once
 
 #include "wg_common.cuh"
@@ -25,13 +28,15 @@ namespace wg {
 constexpr int kRcBT = 32;    // sequences per CTA
 constexpr int kRcMaxQ = 6;   // gate items per thread (BT*H <= kRcMaxQ * threads)
 
-__host__ __device__ inline int recur_hs_stride(int KP) { return ((KP / 4) & 1) ? KP : KP + 4; }
-__host__ __device__ inline int recur_gs_stride(int NP) { return NP + 4; }
-__host__ __device__ inline size_t recur_smem_floats(int KP, int NP, bool w_smem) {
+// hidden state rows hold (h, h) pairs: 2*KP floats (+ pad so 4 consecutive rows hit distinct banks)
+__host__ __device__ inline int recur_hs_stride(int KP) { return ((2 * KP / 4) & 1) ? 2 * KP : 2 * KP + 4; }
+__host__ __device__ inline size_t recur_smem_floats(int KP, int NP, int GP, bool w_smem) {
     size_t n = 0;
     if (w_smem) n += (size_t)KP * NP;
-    n += (size_t)kRcBT * recur_hs_stride(KP);
-    n += (size_t)kRcBT * recur_gs_stride(NP);
+    n += (size_t)kRcBT * recur_hs_stride(KP);  // hs2
+    n += (size_t)kRcBT * GP;                   // gi tile (r,z columns become gi + gh)
+    n += (size_t)kRcBT * KP;                   // gh of the n gate
+    n += (size_t)KP;                           // b_hn
     return n;
 }
 
@@ -43,16 +48,18 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
     constexpr int NT = NWARPS * 32;
     extern __shared__ __align__(16) float smem[];
     const int RS = recur_hs_stride(KP);
-    const int GS = recur_gs_stride(NP);
     float* Ws = smem;
     float* hs = smem + (W_SMEM ? (size_t)KP * NP : 0);
-    float* gs = hs + kRcBT * RS;
+    float* gis = hs + kRcBT * RS;          // [32][ldg]
+    float* ghn = gis + kRcBT * ldg;        // [32][KP]
+    float* bns = ghn + kRcBT * KP;         // [KP]
     const float* Wsrc = W_SMEM ? Ws : WhT;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const long long b0 = (long long)blockIdx.x * kRcBT;
+    const int H2 = 2 * H;
 
     if (W_SMEM) {
         const int n4 = KP * NP / 4;
@@ -61,12 +68,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
         for (int e = tid; e < n4; e += NT) dst[e] = __ldg(src + e);
     }
     for (int e = tid; e < kRcBT * RS; e += NT) hs[e] = 0.0f;
+    for (int e = tid; e < kRcBT * ldg; e += NT) gis[e] = 0.0f;
+    for (int e = tid; e < kRcBT * KP; e += NT) ghn[e] = 0.0f;
+    for (int e = tid; e < KP; e += NT) bns[e] = e < H ? __ldg(bhn + e) : 0.0f;
 
     // ---- gate-phase items of this thread: (b, j) packed as b<<16 | j, j fastest over lanes ----
     const int n_items = kRcBT * H;
     int item_bj[kRcMaxQ];
-    float bn[kRcMaxQ];
-    float gr[kRcMaxQ], gz[kRcMaxQ], gn[kRcMaxQ];
 #pragma unroll
     for (int q = 0; q < kRcMaxQ; ++q) {
         const int item = tid + q * NT;
@@ -77,109 +85,101 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
             if (b0 + b >= B) b = -1;  // ragged last CTA
         }
         item_bj[q] = b < 0 ? -1 : ((b << 16) | j);
-        bn[q] = b < 0 ? 0.0f : __ldg(bhn + j);
-        gr[q] = gz[q] = gn[q] = 0.0f;
     }
-    auto load_gi = [&](int t) {
-#pragma unroll
-        for (int q = 0; q < kRcMaxQ; ++q) {
-            if (item_bj[q] >= 0) {
-                const int b = item_bj[q] >> 16, j = item_bj[q] & 0xffff;
-                const float* p = GI + ((size_t)(b0 + b) * T + t) * ldg + j;
-                gr[q] = __ldg(p);
-                gz[q] = __ldg(p + H);
-                gn[q] = __ldg(p + 2 * H);
-            }
-        }
-    };
-    load_gi(0);
 
     // ---- GEMM-phase coordinates ----
     const int ng = lane & 7;   // column group within the warp tile
     const int bg = lane >> 3;  // row group within the warp tile
-    const int n_ntiles = NP / 32;
-    const int n_tiles = 2 * n_ntiles;
+    const int n_tiles = 2 * (NP / 32);
 
-    __syncthreads();
+    // this thread's part of the gi tile of step t: 4 rows x 16 bytes per warp tile it owns
+    auto prefetch_gi = [&](int t) {
+        for (int wt = warp; wt < n_tiles; wt += NWARPS) {
+            const int wr = wt & 1, nb = wt >> 1;
+            const int nbase = nb * 32 + ng * 4;
+            if (nbase < ldg) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int b = wr * 16 + bg + 4 * i;
+                    if (b0 + b < B)
+                        cp_async16(gis + b * ldg + nbase, GI + ((size_t)(b0 + b) * T + t) * ldg + nbase, true);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    __syncthreads();   // zero fills are done before any async copy may land
+    prefetch_gi(0);
 
     for (int t = 0; t < T; ++t) {
-        // ================= GEMM phase =================
+        // ================= GEMM + merge =================
         for (int wt = warp; wt < n_tiles; wt += NWARPS) {
             const int wr = wt & 1;        // which 16-sequence half
             const int nb = wt >> 1;       // which 32-column block
             const int nbase = nb * 32 + ng * 4;
             const float* hrow = hs + (wr * 16 + bg) * RS;  // rows bg + 4 i
-            float acc[4][4];
+            float2 acc[4][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.0f, 0.0f);
             if (t > 0) {  // h_{-1} = 0: the product is zero at t == 0
 #pragma unroll 2
-                for (int k4 = 0; k4 < KP; k4 += 4) {
-                    float4 hv[4], wv[4];
+                for (int k2 = 0; k2 < KP; k2 += 2) {
+                    float4 hv[4], wv[2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        hv[i] = *reinterpret_cast<const float4*>(hrow + (4 * i) * RS + k4);
+                    for (int i = 0; i < 4; ++i)   // (h[k2], h[k2], h[k2+1], h[k2+1]) of row bg + 4 i
+                        hv[i] = *reinterpret_cast<const float4*>(hrow + (4 * i) * RS + 2 * k2);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const float* wp = Wsrc + (size_t)(k4 + kk) * NP + nbase;
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const float* wp = Wsrc + (size_t)(k2 + kk) * NP + nbase;
                         wv[kk] = W_SMEM ? *reinterpret_cast<const float4*>(wp)
                                         : __ldg(reinterpret_cast<const float4*>(wp));
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        acc[i][0] = fmaf(hv[i].x, wv[0].x, acc[i][0]);
-                        acc[i][1] = fmaf(hv[i].x, wv[0].y, acc[i][1]);
-                        acc[i][2] = fmaf(hv[i].x, wv[0].z, acc[i][2]);
-                        acc[i][3] = fmaf(hv[i].x, wv[0].w, acc[i][3]);
-                        acc[i][0] = fmaf(hv[i].y, wv[1].x, acc[i][0]);
-                        acc[i][1] = fmaf(hv[i].y, wv[1].y, acc[i][1]);
-                        acc[i][2] = fmaf(hv[i].y, wv[1].z, acc[i][2]);
-                        acc[i][3] = fmaf(hv[i].y, wv[1].w, acc[i][3]);
-                        acc[i][0] = fmaf(hv[i].z, wv[2].x, acc[i][0]);
-                        acc[i][1] = fmaf(hv[i].z, wv[2].y, acc[i][1]);
-                        acc[i][2] = fmaf(hv[i].z, wv[2].z, acc[i][2]);
-                        acc[i][3] = fmaf(hv[i].z, wv[2].w, acc[i][3]);
-                        acc[i][0] = fmaf(hv[i].w, wv[3].x, acc[i][0]);
-                        acc[i][1] = fmaf(hv[i].w, wv[3].y, acc[i][1]);
-                        acc[i][2] = fmaf(hv[i].w, wv[3].z, acc[i][2]);
-                        acc[i][3] = fmaf(hv[i].w, wv[3].w, acc[i][3]);
+                        const float2 h0 = make_float2(hv[i].x, hv[i].y), h1 = make_float2(hv[i].z, hv[i].w);
+                        acc[i][0] = __ffma2_rn(h0, make_float2(wv[0].x, wv[0].y), acc[i][0]);
+                        acc[i][1] = __ffma2_rn(h0, make_float2(wv[0].z, wv[0].w), acc[i][1]);
+                        acc[i][0] = __ffma2_rn(h1, make_float2(wv[1].x, wv[1].y), acc[i][0]);
+                        acc[i][1] = __ffma2_rn(h1, make_float2(wv[1].z, wv[1].w), acc[i][1]);
                     }
                 }
             }
+            cp_async_wait<0>();  // this thread's chunks of gi(t) have landed
+            if (nbase < ldg) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                *reinterpret_cast<float4*>(gs + (wr * 16 + bg + 4 * i) * GS + nbase) = v;
+                for (int i = 0; i < 4; ++i) {
+                    const int b = wr * 16 + bg + 4 * i;
+                    float* g = gis + b * ldg + nbase;
+                    const float a4[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int n = nbase + c;
+                        if (n < H2) g[c] += a4[c];                       // r, z: gi + gh
+                        else if (n < 3 * H) ghn[b * KP + (n - H2)] = a4[c];  // n gate: keep gh apart
+                    }
+                }
             }
         }
         __syncthreads();
 
         // ================= gate phase =================
-        float cr[kRcMaxQ], cz[kRcMaxQ], cn[kRcMaxQ];
-#pragma unroll
-        for (int q = 0; q < kRcMaxQ; ++q) {
-            cr[q] = gr[q];
-            cz[q] = gz[q];
-            cn[q] = gn[q];
-        }
-        if (t + 1 < T) load_gi(t + 1);  // in flight during the gates and the next GEMM phase
 #pragma unroll
         for (int q = 0; q < kRcMaxQ; ++q) {
             if (item_bj[q] >= 0) {
                 const int b = item_bj[q] >> 16, j = item_bj[q] & 0xffff;
-                const float* g = gs + b * GS + j;
-                const float r = sigmoid_f(cr[q] + g[0]);
-                const float z = sigmoid_f(cz[q] + g[H]);
-                const float n = tanh_f(cn[q] + r * (g[2 * H] + bn[q]));
-                const float hold = hs[b * RS + j];
+                const float* g = gis + b * ldg + j;
+                const float r = sigmoid_f(g[0]);
+                const float z = sigmoid_f(g[H]);
+                const float n = tanh_f(g[H2] + r * (ghn[b * KP + j] + bns[j]));
+                const float hold = hs[b * RS + 2 * j];
                 const float hnew = (hold - n) * z + n;
-                hs[b * RS + j] = hnew;
+                *reinterpret_cast<float2*>(hs + b * RS + 2 * j) = make_float2(hnew, hnew);
                 out[((size_t)(b0 + b) * T + t) * H + j] = hnew;
             }
         }
         __syncthreads();
+        if (t + 1 < T) prefetch_gi(t + 1);  // lands during the next GEMM
     }
 }
 
