@@ -21,15 +21,15 @@ __global__ void probe(const int* __restrict__ lane_off, float* out, int iters, l
             if (VEC == 4) {
                 float x, y, z, w;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
-                acc0 += x; acc1 += w;
+                acc0 = __int_as_float(__float_as_int(acc0) ^ __float_as_int(x));
             } else if (VEC == 2) {
                 float x, y;
                 asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(x), "=f"(y) : "r"(a));
-                acc0 += x; acc1 += y;
+                acc0 = __int_as_float(__float_as_int(acc0) ^ __float_as_int(x));
             } else {
                 float x;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a));
-                acc0 += x;
+                acc0 = __int_as_float(__float_as_int(acc0) ^ __float_as_int(x));
             }
         }
     }
@@ -41,7 +41,7 @@ __global__ void probe(const int* __restrict__ lane_off, float* out, int iters, l
 struct Pattern { const char* name; int vec; int off[32]; };
 
 int main() {
-    Pattern pats[16];
+    Pattern pats[24];
     int np = 0;
     auto add = [&](const char* n, int vec, auto f) {
         pats[np].name = n; pats[np].vec = vec;
@@ -56,6 +56,9 @@ int main() {
     add("v4 8 distinct, 2 per quarter (lane>>2)*4", 4, [](int l) { return (l >> 2) * 4; });
     add("v4 2 distinct per quarter, 4 rows stride 20 (lane>>3)*20", 4, [](int l) { return (l >> 3) * 20; });
     add("v4 8 rows stride 20 (lane&7)*20", 4, [](int l) { return (l & 7) * 20; });
+    add("v4 rows stride 212, 4 rows (lane>>3)*212 [recur hs]", 4, [](int l) { return (l >> 3) * 212; });
+    add("v4 conflict: 8 rows stride 32 (lane&7)*32", 4, [](int l) { return (l & 7) * 32; });
+    add("v4 16 distinct contiguous (lane>>1)*4", 4, [](int l) { return (l >> 1) * 4; });
     add("v2 4 distinct (lane>>3)*2", 2, [](int l) { return (l >> 3) * 2; });
     add("v2 8 distinct (lane&7)*2", 2, [](int l) { return (l & 7) * 2; });
     add("v2 all distinct lane*2", 2, [](int l) { return l * 2; });

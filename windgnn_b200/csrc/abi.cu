@@ -143,27 +143,34 @@ __global__ void pack_params_kernel(const float* __restrict__ w_ih, const float* 
 // ---------------------------------------------------------------------------------------------
 // stage launchers
 // ---------------------------------------------------------------------------------------------
-template <int FP, int SG, int LAYERS, bool TILED>
+template <int FP, int SG, bool EXACT, int LAYERS, bool TILED>
 int launch_gcn_t(const float* X, const float* adj, const float* W1, const float* b1, const float* W2,
                  const float* b2, float* out, long long R, int S, int Fi, int Fh, int Fo, int ldo,
                  cudaStream_t st) {
     const int NSG = wg::ceil_div(S, SG);
     if (NSG > wg::kGcnThreads)
         return fail(WG_ERR_UNSUPPORTED, "S=%d too large for the dense GCN kernel", S);
+    int Fmax = Fi > Fh ? Fi : Fh;
+    if (LAYERS == 2 && Fo > Fmax) Fmax = Fo;
+    // rows per block: as many as the 128 threads cover, rounded down so that whole blocks are
+    // 16-byte multiples (bulk-copyable): RB * S * Fi % 4 == 0
     int RB = wg::kGcnThreads / NSG;
-    size_t smem = wg::gcn_smem_floats<FP, SG>(S, RB) * 4;
+    const int in_cols = S * Fi;
+    const int need = (in_cols % 4 == 0) ? 1 : (in_cols % 2 == 0 ? 2 : 4);
+    if (RB > need) RB -= RB % need;
+    size_t smem = wg::gcn_smem_floats<FP, SG>(S, Fmax, RB) * 4;
     // aim for >= 3 resident CTAs per SM when the slabs allow it
-    while (smem > (size_t)wg::kMaxSmemOptin / 3 && RB > 8) {
-        RB = RB - (RB + 7) / 8;
-        smem = wg::gcn_smem_floats<FP, SG>(S, RB) * 4;
+    while (smem > (size_t)wg::kMaxSmemOptin / 3 && RB > 2 * need && RB > 8) {
+        RB -= need > (RB + 7) / 8 ? need : (RB + 7) / 8 / need * need;
+        smem = wg::gcn_smem_floats<FP, SG>(S, Fmax, RB) * 4;
     }
     while (smem > (size_t)wg::kMaxSmemOptin && RB > 1) {
         RB = RB / 2;
-        smem = wg::gcn_smem_floats<FP, SG>(S, RB) * 4;
+        smem = wg::gcn_smem_floats<FP, SG>(S, Fmax, RB) * 4;
     }
     if (smem > (size_t)wg::kMaxSmemOptin)
         return fail(WG_ERR_UNSUPPORTED, "dense GCN needs %zu B of shared memory (S=%d); use the sparse path", smem, S);
-    auto kern = wg::gcn_kernel<FP, SG, LAYERS, TILED>;
+    auto kern = wg::gcn_kernel<FP, SG, EXACT, LAYERS, TILED>;
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     WG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wg::kGcnThreads, smem));
@@ -187,11 +194,10 @@ int launch_gcn(const float* X, const float* adj, const float* W1, const float* b
                const float* b2, float* out, long long R, int S, int Fi, int Fh, int Fo, int ldo,
                cudaStream_t st) {
     const int fmax = Fi > Fh ? (Fi > Fo ? Fi : Fo) : (Fh > Fo ? Fh : Fo);
-#define WG_GCN(FP, SG) launch_gcn_t<FP, SG, LAYERS, TILED>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, st)
-    if (fmax <= 13) {
-        return pick_sg(S) == 7 ? WG_GCN(13, 7) : WG_GCN(13, 4);
-    }
-    if (fmax <= 16) return WG_GCN(16, 4);
+#define WG_GCN(FP, SG, EX) \
+    launch_gcn_t<FP, SG, EX, LAYERS, TILED>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, st)
+    if (Fi == 13 && Fh == 13 && Fo == 13) return pick_sg(S) == 7 ? WG_GCN(13, 7, true) : WG_GCN(13, 4, true);
+    if (fmax <= 16) return WG_GCN(16, 4, false);
 #undef WG_GCN
     return fail(WG_ERR_UNSUPPORTED, "GCN feature width %d > 16 is not built into the dense kernel", fmax);
 }
@@ -227,10 +233,13 @@ int launch_recur_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream
 
 template <bool WS>
 int launch_recur_ws(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
-    const int tiles = 2 * (p.NPR / 32);
-    const int for_gates = wg::ceil_div(wg::kRcBT * p.H, wg::kRcMaxQ * 32);
-    int need = tiles < 32 ? tiles : 32;
-    if (for_gates > need) need = for_gates;
+    // warps per 16-sequence group: one per 32-column block (capped), and enough threads for the
+    // gate items (16 * H <= kRcMaxQ * 32 * warps); the CTA runs two groups
+    const int blocks = p.NPR / 32;
+    const int for_gates = wg::ceil_div((wg::kRcBT / 2) * p.H, wg::kRcMaxQ * 32);
+    int wg_warps = blocks < 16 ? blocks : 16;
+    if (for_gates > wg_warps) wg_warps = for_gates;
+    const int need = 2 * wg_warps;
     if (need <= 4) return launch_recur_t<4, WS>(p, ws, out, Bc, st);
     if (need <= 8) return launch_recur_t<8, WS>(p, ws, out, Bc, st);
     if (need <= 12) return launch_recur_t<12, WS>(p, ws, out, Bc, st);

@@ -5,14 +5,15 @@
 // `.view(1, T, S*13)` (:20) is the flat index s*F_out + f used for the output columns here.
 //
 // Work decomposition (dense A_hat, S small enough for A_hat^T to sit in shared memory):
-//   * a CTA owns RB consecutive rows (a row = one (sequence, timestep) pair = an [S, F] slab)
-//     held in ONE shared-memory buffer, features padded to 16 floats per station so a station's
-//     feature vector is four LDS.128; both layers run in place (aggregate -> barrier -> write);
+//   * a CTA owns RB consecutive rows (a row = one (sequence, timestep) pair = an [S, F] slab).
+//     The row block is contiguous in HBM in exactly the layout the kernel computes on, so it is
+//     fetched with ONE bulk async copy (cp.async.bulk, the 1-D TMA path) completing on an
+//     mbarrier; both layers then run in place in that buffer (aggregate -> barrier -> write);
 //   * a thread owns SG consecutive stations of one row and keeps their aggregate in registers
 //     as FEATURE pairs: the S-long aggregation is packed FP32 FMAs (FFMA2, sm_100a: two fp32
-//     FMAs per instruction) acc2[s][fp] += (A[s][s'], A[s][s']) * (x[s'][2fp], x[s'][2fp+1]),
-//     the feature pairs coming straight out of the slab's LDS.128; the F x F transform is FFMA2
-//     too (pairs along the contracted feature index, two partial sums added at the end);
+//     FMAs per instruction) acc2[s][fp] += (A[s][s'], A[s][s']) * (x[s'][2fp], x[s'][2fp+1]);
+//     the F x F transform is FFMA2 too (pairs along the contracted feature index, two partial
+//     sums added at the end);
 //   * only the final slab goes to HBM: either row-major (single-layer op) or, for the fused
 //     path, in the K-major 128-row tiles the input-projection GEMM copies with one bulk
 //     async copy per stage (inproj.cuh), zero-padded to `ldo` columns.
@@ -26,35 +27,35 @@ constexpr int kGcnThreads = 128;
 #ifndef WG_GCN_MINB
 #define WG_GCN_MINB 3  // resident CTAs per SM the register budget is planned for (<= 168 regs)
 #endif
-constexpr int kGcnFS = 16;   // floats per station in the shared slab
+constexpr int kGcnFS = 16;   // feature slots of the packed weight table
 constexpr int kUTileRows = 128;  // rows per K-major tile of the tiled output (= inproj BM)
 
-__host__ __device__ inline int gcn_row_stride(int S) { return S * kGcnFS + 4; }
+// floats of one row slab in shared memory: S stations x the widest feature dim of the layers
+__host__ __device__ inline int gcn_row_stride(int S, int Fmax) { return S * Fmax; }
 
 template <int FP, int SG>
-__host__ __device__ inline size_t gcn_smem_floats(int S, int RB) {
+__host__ __device__ inline size_t gcn_smem_floats(int S, int Fmax, int RB) {
     const int NSG = ceil_div(S, SG);
     size_t n = 0;
     n += (size_t)S * NSG * 8;           // adjT: [S][NSG][8] (SG <= 8 stations per group)
     n += 2 * (size_t)kGcnFS * kGcnFS;   // w1p, w2p: [fp][fo][2] feature-pair weights
     n += 2 * (size_t)kGcnFS;            // b1, b2
-    n += (size_t)RB * gcn_row_stride(S);
+    n += (size_t)round_up(RB * gcn_row_stride(S, Fmax), 4) + 4;  // slab block (+ mbarrier)
     return n;
 }
 
 // One GCN layer on the CTA's row block, in place in shared memory.
-//   buf   [rows][S][16] (+4 pad per row): features of the layer input, overwritten by its output
+//   buf   [rows][RS]: a row holds [S][Fi] on entry and [S][Fo] on exit (RS >= S * max(Fi, Fo))
 //   adjT  [S][NSG][8]: adjT[sp][q][i] = A_hat[q*SG+i][sp] (zero where out of range)
 //   Wp    [8][16][2]: Wp[fp][fo] = (W[2fp][fo], W[2fp+1][fo]) (zero padded)
 // Packed math: the aggregate is kept as FEATURE pairs, acc2[s][fp] = (agg[s][2fp], agg[s][2fp+1]):
-//   aggregation  acc2[s][fp] += (A[s][s'], A[s][s']) * (x[s'][2fp], x[s'][2fp+1])   (x pairs come
-//                straight out of the LDS.128 of the slab, one broadcast MOV per station)
+//   aggregation  acc2[s][fp] += (A[s][s'], A[s][s']) * (x[s'][2fp], x[s'][2fp+1])
 //   transform    o2[s][fo]  += acc2[s][fp] * (W[2fp][fo], W[2fp+1][fo]);  out = o2.x + o2.y + b
-template <int FP, int SG>
+template <int FP, int SG, bool EXACT>
 __device__ __noinline__ void gcn_layer_inplace(float* __restrict__ buf, const float* __restrict__ adjT,
-                                                  const float* __restrict__ Wp,
-                                                  const float* __restrict__ bias, int S, int Fo, int NSG,
-                                                  int row_local, int q, bool active) {
+                                               const float* __restrict__ Wp, const float* __restrict__ bias,
+                                               int S, int Fi, int Fo, int RS, int NSG, int row_local, int q,
+                                               bool active) {
     constexpr int FPP = (FP + 1) / 2;  // feature pairs
     float2 acc[SG][FPP];
     if (active) {
@@ -62,7 +63,7 @@ __device__ __noinline__ void gcn_layer_inplace(float* __restrict__ buf, const fl
         for (int i = 0; i < SG; ++i)
 #pragma unroll
             for (int fp = 0; fp < FPP; ++fp) acc[i][fp] = make_float2(0.0f, 0.0f);
-        const float* xrow = buf + (size_t)row_local * gcn_row_stride(S);
+        const float* xrow = buf + (size_t)row_local * RS;
         const float* arow = adjT + q * 8;
         const int astride = NSG * 8;
 #pragma unroll 1
@@ -76,24 +77,22 @@ __device__ __noinline__ void gcn_layer_inplace(float* __restrict__ buf, const fl
                     a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
                 }
             }
-            float2 xp[8];
+            float x[2 * FPP];
 #pragma unroll
-            for (int v = 0; v < (FPP + 1) / 2; ++v) {
-                const float4 t = *reinterpret_cast<const float4*>(xrow + sp * kGcnFS + 4 * v);
-                xp[2 * v] = make_float2(t.x, t.y);
-                xp[2 * v + 1] = make_float2(t.z, t.w);
-            }
+            for (int f = 0; f < 2 * FPP; ++f)
+                x[f] = (f < FP && (EXACT || f < Fi)) ? xrow[sp * Fi + f] : 0.0f;
 #pragma unroll
             for (int i = 0; i < SG; ++i) {
                 const float2 aa = make_float2(a[i], a[i]);
 #pragma unroll
-                for (int fp = 0; fp < FPP; ++fp) acc[i][fp] = __ffma2_rn(aa, xp[fp], acc[i][fp]);
+                for (int fp = 0; fp < FPP; ++fp)
+                    acc[i][fp] = __ffma2_rn(aa, make_float2(x[2 * fp], x[2 * fp + 1]), acc[i][fp]);
             }
         }
     }
     __syncthreads();  // every thread has finished reading the input slab
     if (active) {
-        float* orow = buf + (size_t)row_local * gcn_row_stride(S) + q * SG * kGcnFS;
+        float* orow = buf + (size_t)row_local * RS + q * SG * Fo;
 #pragma unroll 1
         for (int fo0 = 0; fo0 < Fo; fo0 += 2) {
             float2 o[SG][2];
@@ -109,14 +108,17 @@ __device__ __noinline__ void gcn_layer_inplace(float* __restrict__ buf, const fl
                 }
             }
             const float2 bb = *reinterpret_cast<const float2*>(bias + fo0);
+            const bool two = fo0 + 1 < Fo;
 #pragma unroll
             for (int i = 0; i < SG; ++i) {
                 float u0 = (o[i][0].x + o[i][0].y) + bb.x;
                 float u1 = (o[i][1].x + o[i][1].y) + bb.y;
                 u0 = u0 < 0.0f ? 0.0f : u0;  // ReLU; NaN propagates like torch.relu
                 u1 = u1 < 0.0f ? 0.0f : u1;
-                // an odd Fo writes one extra column: relu(0 + 0) = 0 into the station's pad lanes
-                if (q * SG + i < S) *reinterpret_cast<float2*>(orow + i * kGcnFS + fo0) = make_float2(u0, u1);
+                if (q * SG + i < S) {
+                    orow[i * Fo + fo0] = u0;
+                    if (two) orow[i * Fo + fo0 + 1] = u1;
+                }
             }
         }
     }
@@ -126,7 +128,7 @@ __device__ __noinline__ void gcn_layer_inplace(float* __restrict__ buf, const fl
 // LAYERS == 2: GCN2(GCN1(x)) ; LAYERS == 1: GCN1(x) (W2/b2 unused, pass Fh = Fo = output width).
 // TILED: out is [ceil(R/128)][ldo][128] (K-major row tiles, zero padded columns) else [R][ldo]
 // row-major with ldo == S * F_last.
-template <int FP, int SG, int LAYERS, bool TILED>
+template <int FP, int SG, bool EXACT, int LAYERS, bool TILED>
 __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
     gcn_kernel(const float* __restrict__ X, const float* __restrict__ adj, const float* __restrict__ W1,
                const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
@@ -135,7 +137,9 @@ __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
     const int NSG = ceil_div(S, SG);
     const int tid = threadIdx.x;
     const int Flast = LAYERS == 2 ? Fo : Fh;
-    const int RS = gcn_row_stride(S);
+    int Fmax = Fi > Fh ? Fi : Fh;
+    if (LAYERS == 2 && Fo > Fmax) Fmax = Fo;
+    const int RS = gcn_row_stride(S, Fmax);
 
     float* adjT = smem;
     float* w1d = adjT + (size_t)S * NSG * 8;
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
     float* b1s = w2d + kGcnFS * kGcnFS;
     float* b2s = b1s + kGcnFS;
     float* buf = b2s + kGcnFS;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(buf + round_up(RB * RS, 4));
 
     // ---- stage the (tiny) graph and layer parameters once per CTA ----
     for (int e = tid; e < S * NSG * 8; e += kGcnThreads) {
@@ -163,8 +168,10 @@ __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
         b1s[e] = e < Fh ? b1[e] : 0.0f;
         b2s[e] = (LAYERS == 2 && e < Fo) ? b2[e] : 0.0f;
     }
-    // the slab's pad lanes (f >= F) must hold finite values: they meet zero weights
-    for (int e = tid; e < RB * RS; e += kGcnThreads) buf[e] = 0.0f;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
     __syncthreads();
 
     const int row_local = tid / NSG;
@@ -172,31 +179,38 @@ __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
     const long long nblocks = (R + RB - 1) / RB;
     const int in_cols = S * Fi;
     const int out_cols = S * Flast;
-    // per-thread stepping of (row, station, feature) by kGcnThreads elements of the input block
-    const int step_rs = kGcnThreads / Fi, step_f = kGcnThreads % Fi;
+    // when the slab row is exactly one input row the block is one contiguous, TMA-copyable span
+    const bool dense_rows = (RS == in_cols);
+    unsigned phase = 0;
 
     for (long long rb = blockIdx.x; rb < nblocks; rb += gridDim.x) {
         const long long r0 = rb * RB;
         const int nrows = (int)((R - r0) < RB ? (R - r0) : RB);
-        // ---- coalesced copy of the row block (contiguous in HBM) into the padded slab ----
-        {
-            const float* src = X + (size_t)r0 * in_cols;
-            const int n_in = nrows * in_cols;
-            int f = tid % Fi, rs = tid / Fi;          // rs = row * S + station
-            int row = rs / S, st = rs - row * S;
-            for (int e = tid; e < n_in; e += kGcnThreads) {
-                buf[row * RS + st * kGcnFS + f] = __ldg(src + e);
-                f += step_f;
-                st += step_rs;
-                if (f >= Fi) { f -= Fi; ++st; }
-                while (st >= S) { st -= S; ++row; }
+        const float* src = X + (size_t)r0 * in_cols;
+        const size_t bytes = (size_t)nrows * in_cols * 4;
+        const bool bulk = dense_rows && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0);
+        if (bulk) {
+            // ---- one bulk async copy of the whole row block, completion on the mbarrier ----
+            if (tid == 0) {
+                mbar_expect_tx(bar, (unsigned)bytes);
+                bulk_g2s(buf, src, (unsigned)bytes, bar);
             }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            // ---- ragged / unaligned block: coalesced element copy ----
+            const int n_in = nrows * in_cols;
+            for (int e = tid; e < n_in; e += kGcnThreads) {
+                const int row = e / in_cols;
+                buf[row * RS + (e - row * in_cols)] = __ldg(src + e);
+            }
+            __syncthreads();
         }
-        __syncthreads();
 
         const bool active = row_local < nrows;
-        gcn_layer_inplace<FP, SG>(buf, adjT, w1d, b1s, S, Fh, NSG, row_local, q, active);
-        if (LAYERS == 2) gcn_layer_inplace<FP, SG>(buf, adjT, w2d, b2s, S, Fo, NSG, row_local, q, active);
+        gcn_layer_inplace<FP, SG, EXACT>(buf, adjT, w1d, b1s, S, Fi, Fh, RS, NSG, row_local, q, active);
+        if (LAYERS == 2)
+            gcn_layer_inplace<FP, SG, EXACT>(buf, adjT, w2d, b2s, S, Fh, Fo, RS, NSG, row_local, q, active);
 
         // ---- store the final slab ----
         if (TILED) {
@@ -204,27 +218,23 @@ __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
             const int n_out = nrows * ldo;
             int rl = tid % nrows, c = tid / nrows;
             const int step_c = kGcnThreads / nrows, step_r = kGcnThreads % nrows;
-            int st = c / Flast, f = c - st * Flast;
             for (int e = tid; e < n_out; e += kGcnThreads) {
                 const long long r = r0 + rl;
-                const float v = c < out_cols ? buf[rl * RS + st * kGcnFS + f] : 0.0f;
+                const float v = c < out_cols ? buf[rl * RS + c] : 0.0f;
                 out[((size_t)(r / kUTileRows) * ldo + c) * kUTileRows + (r % kUTileRows)] = v;
                 rl += step_r;
                 c += step_c;
                 if (rl >= nrows) { rl -= nrows; ++c; }
-                st = c / Flast;
-                f = c - st * Flast;
             }
         } else {
             float* dst = out + (size_t)r0 * ldo;
             const int n_out = nrows * ldo;
             for (int e = tid; e < n_out; e += kGcnThreads) {
-                const int row = e / ldo, c = e - row * ldo;
-                const int st = c / Flast, f = c - st * Flast;
-                dst[e] = buf[row * RS + st * kGcnFS + f];
+                const int row = e / ldo;
+                dst[e] = buf[row * RS + (e - row * ldo)];
             }
         }
-        __syncthreads();
+        __syncthreads();  // the slab is free again (generic reads done before the next async write)
     }
 }
 
