@@ -58,7 +58,7 @@ struct Plan {
     int NPB;       // rows of packed w_ih: G rounded up to 64
     int GP;        // leading dim of GI: G rounded up to 4
     int KP;        // K of the recurrent GEMM: H rounded up to 4
-    int NPR;       // columns of packed w_hh^T: G rounded up to 32
+    int NPR;       // columns of packed w_hh^T: G rounded up to 80 (one warp's column block)
     size_t off_wp, off_bias, off_wht, off_bhn, off_u, off_gi, total;
 };
 
@@ -82,7 +82,7 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     p.NPB = wg::round_up(p.G, wg::kIpBN);
     p.GP = wg::round_up(p.G, 4);
     p.KP = wg::round_up(H, 4);
-    p.NPR = wg::round_up(p.G, 32);
+    p.NPR = wg::recur_np(p.G);
     size_t o = 0;
     p.off_wp = o;   o = align_up(o + (size_t)p.NPB * p.IP * 4);
     p.off_bias = o; o = align_up(o + (size_t)p.NPB * 4);
@@ -233,22 +233,16 @@ int launch_recur_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream
 
 template <bool WS>
 int launch_recur_ws(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
-    // warps per 16-sequence group: one per 32-column block (capped), and enough threads for the
-    // gate items (16 * H <= kRcMaxQ * 32 * warps); the CTA runs two groups
-    const int blocks = p.NPR / 32;
-    const int for_gates = wg::ceil_div((wg::kRcBT / 2) * p.H, wg::kRcMaxQ * 32);
-    int wg_warps = blocks < 16 ? blocks : 16;
-    if (for_gates > wg_warps) wg_warps = for_gates;
-    const int need = 2 * wg_warps;
-    if (need <= 4) return launch_recur_t<4, WS>(p, ws, out, Bc, st);
-    if (need <= 8) return launch_recur_t<8, WS>(p, ws, out, Bc, st);
-    if (need <= 12) return launch_recur_t<12, WS>(p, ws, out, Bc, st);
-    if (need <= 16) return launch_recur_t<16, WS>(p, ws, out, Bc, st);
-    if (need <= 20) return launch_recur_t<20, WS>(p, ws, out, Bc, st);
-    if (need <= 24) return launch_recur_t<24, WS>(p, ws, out, Bc, st);
-    if (need <= 32) return launch_recur_t<32, WS>(p, ws, out, Bc, st);
-    return fail(WG_ERR_UNSUPPORTED, "GRU hidden size %d too large for the recurrence kernel (max %d)",
-                p.H, wg::kRcMaxQ * 1024 / wg::kRcBT);
+    // warps per 16-sequence group: one per 80-column block (1, 2, 4 or 8; more blocks are looped).
+    // kRcMaxQ = 14 gate items per thread always suffices: 16 H <= 14 * 32 * ceil(3H / 80).
+    const int blocks = p.NPR / wg::kRcCB;
+    if ((wg::kRcBT / 2) * p.H > wg::kRcMaxQ * 32 * 8)
+        return fail(WG_ERR_UNSUPPORTED, "GRU hidden size %d too large for the recurrence kernel (max %d)",
+                    p.H, wg::kRcMaxQ * 32 * 8 / (wg::kRcBT / 2));
+    if (blocks <= 1) return launch_recur_t<2, WS>(p, ws, out, Bc, st);
+    if (blocks <= 2) return launch_recur_t<4, WS>(p, ws, out, Bc, st);
+    if (blocks <= 4) return launch_recur_t<8, WS>(p, ws, out, Bc, st);
+    return launch_recur_t<16, WS>(p, ws, out, Bc, st);
 }
 
 int launch_recur(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {

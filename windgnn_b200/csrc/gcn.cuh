@@ -38,7 +38,7 @@ __host__ __device__ inline size_t gcn_smem_floats(int S, int Fmax, int RB) {
     const int NSG = ceil_div(S, SG);
     size_t n = 0;
     n += (size_t)S * NSG * 8;           // adjT: [S][NSG][8] (SG <= 8 stations per group)
-    n += 2 * (size_t)kGcnFS * kGcnFS;   // w1p, w2p: [fp][fo][2] feature-pair weights
+    n += 2 * (size_t)kGcnFS * kGcnFS;   // w1, w2: [f][fo] zero padded to 16 x 16
     n += 2 * (size_t)kGcnFS;            // b1, b2
     n += (size_t)round_up(RB * gcn_row_stride(S, Fmax), 4) + 4;  // slab block (+ mbarrier)
     return n;
@@ -47,13 +47,13 @@ __host__ __device__ inline size_t gcn_smem_floats(int S, int Fmax, int RB) {
 // One GCN layer on the CTA's row block, in place in shared memory.
 //   buf   [rows][RS]: a row holds [S][Fi] on entry and [S][Fo] on exit (RS >= S * max(Fi, Fo))
 //   adjT  [S][NSG][8]: adjT[sp][q][i] = A_hat[q*SG+i][sp] (zero where out of range)
-//   Wp    [8][16][2]: Wp[fp][fo] = (W[2fp][fo], W[2fp+1][fo]) (zero padded)
-// Packed math: the aggregate is kept as FEATURE pairs, acc2[s][fp] = (agg[s][2fp], agg[s][2fp+1]):
-//   aggregation  acc2[s][fp] += (A[s][s'], A[s][s']) * (x[s'][2fp], x[s'][2fp+1])
-//   transform    o2[s][fo]  += acc2[s][fp] * (W[2fp][fo], W[2fp+1][fo]);  out = o2.x + o2.y + b
+//   Wn    [16][16]: Wn[f][fo] = W[f][fo] (zero padded)
+// Packed math (FFMA2 takes one operand as a scalar that it broadcasts to both halves):
+//   aggregation  acc2[s][(f, f+1)]  += A[s][s']  * (x[s'][f], x[s'][f+1])
+//   transform    o2[s][(fo, fo+1)]  += agg[s][f] * (W[f][fo], W[f][fo+1])
 template <int FP, int SG, bool EXACT>
 __device__ __noinline__ void gcn_layer_inplace(float* __restrict__ buf, const float* __restrict__ adjT,
-                                               const float* __restrict__ Wp, const float* __restrict__ bias,
+                                               const float* __restrict__ Wn, const float* __restrict__ bias,
                                                int S, int Fi, int Fo, int RS, int NSG, int row_local, int q,
                                                bool active) {
     constexpr int FPP = (FP + 1) / 2;  // feature pairs
@@ -92,32 +92,34 @@ __device__ __noinline__ void gcn_layer_inplace(float* __restrict__ buf, const fl
     }
     __syncthreads();  // every thread has finished reading the input slab
     if (active) {
+        // transform: o2[s][(fo, fo+1)] += agg[s][f] (scalar operand, broadcast by FFMA2) * (W[f][fo], W[f][fo+1])
         float* orow = buf + (size_t)row_local * RS + q * SG * Fo;
 #pragma unroll 1
-        for (int fo0 = 0; fo0 < Fo; fo0 += 2) {
+        for (int fo0 = 0; fo0 < Fo; fo0 += 4) {
             float2 o[SG][2];
 #pragma unroll
             for (int i = 0; i < SG; ++i) o[i][0] = o[i][1] = make_float2(0.0f, 0.0f);
+            const bool second = fo0 + 2 < Fo;  // the chunk's upper fo pair exists
 #pragma unroll
-            for (int fp = 0; fp < FPP; ++fp) {
-                const float4 w = *reinterpret_cast<const float4*>(Wp + (fp * kGcnFS + fo0) * 2);
+            for (int f = 0; f < FP; ++f) {
+                const float4 w = *reinterpret_cast<const float4*>(Wn + f * kGcnFS + fo0);
 #pragma unroll
                 for (int i = 0; i < SG; ++i) {
-                    o[i][0] = __ffma2_rn(acc[i][fp], make_float2(w.x, w.y), o[i][0]);
-                    o[i][1] = __ffma2_rn(acc[i][fp], make_float2(w.z, w.w), o[i][1]);
+                    const float av = (f & 1) ? acc[i][f >> 1].y : acc[i][f >> 1].x;
+                    o[i][0] = __ffma2_rn(make_float2(av, av), make_float2(w.x, w.y), o[i][0]);
+                    if (second) o[i][1] = __ffma2_rn(make_float2(av, av), make_float2(w.z, w.w), o[i][1]);
                 }
             }
-            const float2 bb = *reinterpret_cast<const float2*>(bias + fo0);
-            const bool two = fo0 + 1 < Fo;
+            const float4 bb = *reinterpret_cast<const float4*>(bias + fo0);
 #pragma unroll
             for (int i = 0; i < SG; ++i) {
-                float u0 = (o[i][0].x + o[i][0].y) + bb.x;
-                float u1 = (o[i][1].x + o[i][1].y) + bb.y;
-                u0 = u0 < 0.0f ? 0.0f : u0;  // ReLU; NaN propagates like torch.relu
-                u1 = u1 < 0.0f ? 0.0f : u1;
                 if (q * SG + i < S) {
-                    orow[i * Fo + fo0] = u0;
-                    if (two) orow[i * Fo + fo0 + 1] = u1;
+                    float* op = orow + i * Fo + fo0;
+                    float u;
+                    u = o[i][0].x + bb.x; op[0] = u < 0.0f ? 0.0f : u;  // ReLU; NaN propagates like torch.relu
+                    if (fo0 + 1 < Fo) { u = o[i][0].y + bb.y; op[1] = u < 0.0f ? 0.0f : u; }
+                    if (fo0 + 2 < Fo) { u = o[i][1].x + bb.z; op[2] = u < 0.0f ? 0.0f : u; }
+                    if (fo0 + 3 < Fo) { u = o[i][1].y + bb.w; op[3] = u < 0.0f ? 0.0f : u; }
                 }
             }
         }
@@ -158,9 +160,7 @@ __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
         adjT[e] = (i < SG && s < S) ? adj[(size_t)s * S + sp] : 0.0f;
     }
     for (int e = tid; e < kGcnFS * kGcnFS; e += kGcnThreads) {
-        // e = (fp * 16 + fo) * 2 + h  ->  W[2 fp + h][fo]
-        const int h = e & 1, fo = (e >> 1) % kGcnFS, fp = (e >> 1) / kGcnFS;
-        const int f = 2 * fp + h;
+        const int f = e / kGcnFS, fo = e % kGcnFS;
         w1d[e] = (f < Fi && fo < Fh) ? W1[f * Fh + fo] : 0.0f;
         w2d[e] = (LAYERS == 2 && f < Fh && fo < Fo) ? W2[f * Fo + fo] : 0.0f;
     }
@@ -214,17 +214,14 @@ __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
 
         // ---- store the final slab ----
         if (TILED) {
-            // out[(r / 128)][c][r % 128]; consecutive threads -> consecutive rows of one column
-            const int n_out = nrows * ldo;
-            int rl = tid % nrows, c = tid / nrows;
-            const int step_c = kGcnThreads / nrows, step_r = kGcnThreads % nrows;
-            for (int e = tid; e < n_out; e += kGcnThreads) {
+            // out[(r / 128)][c][r % 128]: a lane owns one row of the block (its tile offset is fixed),
+            // each warp walks the columns; a store instruction writes nrows consecutive floats
+            for (int rl = tid & 31; rl < nrows; rl += 32) {
                 const long long r = r0 + rl;
-                const float v = c < out_cols ? buf[rl * RS + c] : 0.0f;
-                out[((size_t)(r / kUTileRows) * ldo + c) * kUTileRows + (r % kUTileRows)] = v;
-                rl += step_r;
-                c += step_c;
-                if (rl >= nrows) { rl -= nrows; ++c; }
+                float* dstc = out + (size_t)(r / kUTileRows) * ldo * kUTileRows + (r % kUTileRows);
+                const float* srcr = buf + rl * RS;
+                for (int c = tid >> 5; c < ldo; c += kGcnThreads / 32)
+                    dstc[(size_t)c * kUTileRows] = c < out_cols ? srcr[c] : 0.0f;
             }
         } else {
             float* dst = out + (size_t)r0 * ldo;

@@ -12,12 +12,13 @@
 // (read) and h (written) touches HBM inside the time loop.  The warps form TWO independent
 // groups of 16 sequences that only ever synchronise among themselves (named barriers), so one
 // group's gate phase (MUFU-bound) overlaps the other group's GEMM (FMA-bound).  Per step:
-//   GEMM  : acc[b][n] = sum_k h[b][k] * W[k][n] on the FMA pipe with packed FFMA2 (pairs along n;
-//           the hidden state is kept DUPLICATED in shared memory, (h, h), so both FFMA2 operands
-//           are plain LDS.128 register pairs).  Warp tile 16 sequences x 32 gate columns, thread
-//           tile 4 x 4, operand fragments double-buffered in registers.
-//   merge : each thread adds its accumulators onto the gi tile that IT prefetched with cp.async
-//           during the GEMM (16-byte chunks, no barrier needed: a thread only waits for its own
+//   GEMM  : acc[b][n] = sum_k h[b][k] * W[k][n] on the FMA pipe with packed FFMA2 (sm_100a):
+//           acc2[b][(n, n+1)] += h[b][k] (scalar operand, broadcast) * (W[k][n], W[k][n+1]).
+//           A warp covers 16 sequences x 80 gate columns, a thread 4 x 10 (five column pairs);
+//           operand fragments of four k's are double-buffered in registers so the LDS latency
+//           hides behind the previous fragment's 80 FFMA2.
+//   merge : each thread adds its accumulators onto the gi chunks that IT prefetched with
+//           cp.async during the GEMM (no barrier needed: a thread only waits for its own
 //           copies); the n-gate part of gh is kept apart because r multiplies it.
 //   gates : one (sequence, hidden unit) item per thread-slot, lanes along the hidden index so
 //           the h stores to HBM are coalesced.
@@ -27,15 +28,17 @@
 
 namespace wg {
 
-constexpr int kRcBT = 32;    // sequences per CTA
-constexpr int kRcMaxQ = 6;   // gate items per thread (BT*H <= kRcMaxQ * threads)
+constexpr int kRcBT = 32;    // sequences per CTA (two groups of 16)
+constexpr int kRcCB = 80;    // gate columns per warp
+constexpr int kRcMaxQ = 14;  // gate items per thread: 16 * H <= kRcMaxQ * 32 * warps_per_group
 
-// hidden state rows hold (h, h) pairs: 2*KP floats (+ pad so 4 consecutive rows hit distinct banks)
-__host__ __device__ inline int recur_hs_stride(int KP) { return ((2 * KP / 4) & 1) ? 2 * KP : 2 * KP + 4; }
+__host__ __device__ inline int recur_np(int G) { return round_up(G, kRcCB); }
+// hidden-state rows: KP floats padded so that four consecutive rows start in distinct bank groups
+__host__ __device__ inline int recur_hs_stride(int KP) { return ((KP / 4) & 1) ? KP : KP + 4; }
 __host__ __device__ inline size_t recur_smem_floats(int KP, int NP, int GP, bool w_smem) {
     size_t n = 0;
     if (w_smem) n += (size_t)KP * NP;
-    n += (size_t)kRcBT * recur_hs_stride(KP);  // hs2
+    n += (size_t)kRcBT * recur_hs_stride(KP);  // hs
     n += (size_t)kRcBT * GP;                   // gi tile (r,z columns become gi + gh)
     n += (size_t)kRcBT * KP;                   // gh of the n gate
     n += (size_t)KP;                           // b_hn
@@ -45,6 +48,17 @@ __host__ __device__ inline size_t recur_smem_floats(int KP, int NP, int GP, bool
 __device__ __forceinline__ void group_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// one operand fragment: four k's of this thread's 4 rows and 10 columns
+struct RcFrag {
+    float4 h[4];      // h[i] = hs[row i][k .. k+3]
+    float4 wa[4];     // W[k + kk][cA .. cA+3]
+    float4 wb[4];     // W[k + kk][cB .. cB+3]
+    float2 wc[4];     // W[k + kk][cC .. cC+1]
+};
 
 template <int NWARPS, bool W_SMEM>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
@@ -101,21 +115,24 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
     }
 
     // ---- GEMM-phase coordinates ----
-    const int ng = lane & 7;   // column group within the warp tile
-    const int bg = lane >> 3;  // row group within the warp tile
-    const int n_nb = NP / 32;  // 32-column blocks; this warp takes gwarp, gwarp + WG, ...
+    const int ln = lane & 7;   // column slot within the warp's 80 columns
+    const int bg = lane >> 3;  // row group
+    const int n_cb = NP / kRcCB;           // 80-column blocks; this warp takes gwarp, gwarp + WG, ...
     const int rbase = grp * GB + bg;       // rows rbase + 4 i
 
-    // this thread's part of the gi tile of step t: 4 rows x 16 bytes per column block it owns
+    // this thread's chunks of the gi tile of step t: per row 16 + 16 + 8 bytes per column block
     auto prefetch_gi = [&](int t) {
-        for (int nb = gwarp; nb < n_nb; nb += WG) {
-            const int nbase = nb * 32 + ng * 4;
-            if (nbase < ldg) {
+        for (int cb = gwarp; cb < n_cb; cb += WG) {
+            const int cA = cb * kRcCB + ln * 4, cB = cA + 32, cC = cb * kRcCB + 64 + ln * 2;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int b = rbase + 4 * i;
-                    if (b0 + b < B)
-                        cp_async16(gis + b * ldg + nbase, GI + ((size_t)(b0 + b) * T + t) * ldg + nbase, true);
+            for (int i = 0; i < 4; ++i) {
+                const int b = rbase + 4 * i;
+                if (b0 + b < B) {
+                    const float* src = GI + ((size_t)(b0 + b) * T + t) * ldg;
+                    float* dst = gis + b * ldg;
+                    if (cA < ldg) cp_async16(dst + cA, src + cA, true);
+                    if (cB < ldg) cp_async16(dst + cB, src + cB, true);
+                    if (cC < ldg) cp_async8(dst + cC, src + cC);
                 }
             }
         }
@@ -126,66 +143,87 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
     prefetch_gi(0);
 
     const float* hrow = hs + rbase * RS;
+    const int h_step = 4 * RS;
     for (int t = 0; t < T; ++t) {
         // ================= GEMM + merge =================
-        for (int nb = gwarp; nb < n_nb; nb += WG) {
-            const int nbase = nb * 32 + ng * 4;
-            const float* wcol = Wsrc + nbase;
-            float2 acc[4][2];
+        for (int cb = gwarp; cb < n_cb; cb += WG) {
+            const int cA = cb * kRcCB + ln * 4, cB = cA + 32, cC = cb * kRcCB + 64 + ln * 2;
+            float2 acc[4][5];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.0f, 0.0f);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int p = 0; p < 5; ++p) acc[i][p] = make_float2(0.0f, 0.0f);
 
-            auto load_frag = [&](int k2, float4 (&hv)[4], float4 (&wv)[2]) {
+            const float* hp = hrow;            // + 4 floats per fragment
+            const float* wp = Wsrc + cA;       // + 4 * NP floats per fragment
+            auto load_frag = [&](RcFrag& f) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)   // (h[k2], h[k2], h[k2+1], h[k2+1]) of row rbase + 4 i
-                    hv[i] = *reinterpret_cast<const float4*>(hrow + (4 * i) * RS + 2 * k2);
+                for (int i = 0; i < 4; ++i) f.h[i] = *reinterpret_cast<const float4*>(hp + i * h_step);
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const float* wp = wcol + (size_t)(k2 + kk) * NP;
-                    wv[kk] = W_SMEM ? *reinterpret_cast<const float4*>(wp)
-                                    : __ldg(reinterpret_cast<const float4*>(wp));
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float* w = wp + kk * NP;
+                    if (W_SMEM) {
+                        f.wa[kk] = *reinterpret_cast<const float4*>(w);
+                        f.wb[kk] = *reinterpret_cast<const float4*>(w + 32);
+                        f.wc[kk] = *reinterpret_cast<const float2*>(w + 64 - 2 * ln);
+                    } else {
+                        f.wa[kk] = __ldg(reinterpret_cast<const float4*>(w));
+                        f.wb[kk] = __ldg(reinterpret_cast<const float4*>(w + 32));
+                        f.wc[kk] = __ldg(reinterpret_cast<const float2*>(w + 64 - 2 * ln));
+                    }
                 }
+                hp += 4;
+                wp += 4 * NP;
             };
-            auto mma_frag = [&](const float4 (&hv)[4], const float4 (&wv)[2]) {
+            auto mma_frag = [&](const RcFrag& f) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 h0 = make_float2(hv[i].x, hv[i].y), h1 = make_float2(hv[i].z, hv[i].w);
-                    acc[i][0] = __ffma2_rn(h0, make_float2(wv[0].x, wv[0].y), acc[i][0]);
-                    acc[i][1] = __ffma2_rn(h0, make_float2(wv[0].z, wv[0].w), acc[i][1]);
-                    acc[i][0] = __ffma2_rn(h1, make_float2(wv[1].x, wv[1].y), acc[i][0]);
-                    acc[i][1] = __ffma2_rn(h1, make_float2(wv[1].z, wv[1].w), acc[i][1]);
+                for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float hv = kk == 0 ? f.h[i].x : kk == 1 ? f.h[i].y : kk == 2 ? f.h[i].z : f.h[i].w;
+                        const float2 hh = make_float2(hv, hv);  // FFMA2 broadcasts a scalar operand
+                        acc[i][0] = __ffma2_rn(hh, make_float2(f.wa[kk].x, f.wa[kk].y), acc[i][0]);
+                        acc[i][1] = __ffma2_rn(hh, make_float2(f.wa[kk].z, f.wa[kk].w), acc[i][1]);
+                        acc[i][2] = __ffma2_rn(hh, make_float2(f.wb[kk].x, f.wb[kk].y), acc[i][2]);
+                        acc[i][3] = __ffma2_rn(hh, make_float2(f.wb[kk].z, f.wb[kk].w), acc[i][3]);
+                        acc[i][4] = __ffma2_rn(hh, f.wc[kk], acc[i][4]);
+                    }
                 }
             };
             if (t > 0) {  // h_{-1} = 0: the product is zero at t == 0
-                float4 hA[4], wA[2], hB[4], wB[2];
-                load_frag(0, hA, wA);
+                // software pipeline over KP / 4 fragments; branch-free body so the fragment
+                // registers are written by the loads themselves
+                RcFrag fa, fb;
+                load_frag(fa);
+                int k4 = 4;
 #pragma unroll 1
-                for (int k2 = 0; k2 < KP; k2 += 4) {  // KP is a multiple of 4
-                    load_frag(k2 + 2, hB, wB);
-                    mma_frag(hA, wA);
-                    if (k2 + 4 < KP) load_frag(k2 + 4, hA, wA);
-                    mma_frag(hB, wB);
+                for (; k4 + 4 < KP; k4 += 8) {
+                    load_frag(fb);
+                    mma_frag(fa);
+                    load_frag(fa);
+                    mma_frag(fb);
+                }
+                if (k4 < KP) {   // even number of fragments: one more pair
+                    load_frag(fb);
+                    mma_frag(fa);
+                    mma_frag(fb);
+                } else {
+                    mma_frag(fa);
                 }
             }
             cp_async_wait<0>();  // this thread's chunks of gi(t) have landed
-            if (nbase < ldg) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int b = rbase + 4 * i;
-                    float* g = gis + b * ldg + nbase;
-                    const float a4[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
-                    if (nbase + 3 < H2) {          // whole chunk in the r / z gates: gi + gh
-                        float4 v = *reinterpret_cast<float4*>(g);
-                        v.x += a4[0]; v.y += a4[1]; v.z += a4[2]; v.w += a4[3];
-                        *reinterpret_cast<float4*>(g) = v;
-                    } else {
+            for (int i = 0; i < 4; ++i) {
+                const int b = rbase + 4 * i;
+                float* g = gis + b * ldg;
+                float* gn = ghn + b * KP;
+                const float a10[10] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y, acc[i][2].x,
+                                       acc[i][2].y, acc[i][3].x, acc[i][3].y, acc[i][4].x, acc[i][4].y};
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int n = nbase + c;
-                            if (n < H2) g[c] += a4[c];
-                            else if (n < 3 * H) ghn[b * KP + (n - H2)] = a4[c];  // n gate: keep gh apart
-                        }
-                    }
+                for (int c = 0; c < 10; ++c) {
+                    const int n = c < 4 ? cA + c : c < 8 ? cB + (c - 4) : cC + (c - 8);
+                    if (n < H2) g[n] += a10[c];                  // r, z: gi + gh
+                    else if (n < 3 * H) gn[n - H2] = a10[c];     // n gate: keep gh apart
                 }
             }
         }
@@ -200,9 +238,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
                 const float r = sigmoid_f(g[0]);
                 const float z = sigmoid_f(g[H]);
                 const float n = tanh_f(g[H2] + r * (ghn[b * KP + j] + bns[j]));
-                const float hold = hs[b * RS + 2 * j];
+                const float hold = hs[b * RS + j];
                 const float hnew = (hold - n) * z + n;
-                *reinterpret_cast<float2*>(hs + b * RS + 2 * j) = make_float2(hnew, hnew);
+                hs[b * RS + j] = hnew;
                 out[((size_t)(b0 + b) * T + t) * H + j] = hnew;
             }
         }
