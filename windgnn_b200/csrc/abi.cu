@@ -512,6 +512,14 @@ int wg_gcn_layer_f32(const float* adj, const float* attr, const float* weight, c
                                 S * F_out, static_cast<cudaStream_t>(stream));
 }
 
+#ifdef WG_RC_TRACE
+// debug build only (not declared in the public header)
+int wg_debug_read_trace(long long* host, int n) {
+    if (n > 2 * 8 * 256) n = 2 * 8 * 256;
+    return (int)cudaMemcpyFromSymbol(host, wg::g_rc_trace, sizeof(long long) * n);
+}
+#endif
+
 double wg_measure_ffma_tflops(int device, int iters) {
     DeviceGuard g(device);
     if (g.err != cudaSuccess) {

@@ -48,9 +48,29 @@ __host__ __device__ inline size_t recur_smem_floats(int KP, int NP, int GP, bool
 __device__ __forceinline__ void group_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void group_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+
+template <int N>
+struct IntC { static constexpr int value = N; };
+
+#ifndef WG_GATE_EXP
+#define WG_GATE_EXP 0
+#endif
+#ifdef WG_RC_TRACE
+// debug build only: per-phase clock stamps of CTA 0 (8 stamps per step per group)
+__device__ long long g_rc_trace[2 * 8 * 256];
+#define WG_TRACE(slot)                                                                          \
+    do {                                                                                        \
+        if (blockIdx.x == 0 && gtid == 0 && t < 256) g_rc_trace[(grp * 256 + t) * 8 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define WG_TRACE(slot) do { } while (0)
+#endif
 
 // one operand fragment: four k's of this thread's 4 rows and 10 columns
 struct RcFrag {
@@ -144,8 +164,24 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
 
     const float* hrow = hs + rbase * RS;
     const int h_step = 4 * RS;
+#ifndef WG_RC_ALTERNATE
+#define WG_RC_ALTERNATE 1
+#endif
     for (int t = 0; t < T; ++t) {
+        WG_TRACE(0);
+#if WG_RC_ALTERNATE
+        // The two groups take turns on the FMA pipe: group 0 runs GEMM(t) while group 1 does the
+        // merge / gates of step t-1, then they swap.  Barrier 3: "group 0 finished its GEMM",
+        // barrier 4: "group 1 finished its GEMM" (arrive = signal, sync = wait; NT participants).
+        if (grp == 0) {
+            if (t > 0) group_barrier(4, NT);
+        } else {
+            group_barrier(3, NT);
+        }
+#endif
         // ================= GEMM + merge =================
+        WG_TRACE(1);
+        bool handed_over = false;
         for (int cb = gwarp; cb < n_cb; cb += WG) {
             const int cA = cb * kRcCB + ln * 4, cB = cA + 32, cC = cb * kRcCB + 64 + ln * 2;
             float2 acc[4][5];
@@ -211,41 +247,107 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
                     mma_frag(fa);
                 }
             }
+#if WG_RC_ALTERNATE
+            if (cb + WG >= n_cb) {  // last column block of this warp: hand the FMA pipe over
+                if (grp == 0) group_arrive(3, NT);
+                else if (t + 1 < T) group_arrive(4, NT);
+                handed_over = true;
+            }
+#endif
+            WG_TRACE(2);
             cp_async_wait<0>();  // this thread's chunks of gi(t) have landed
+            // merge one aligned chunk of W columns [n0, n0 + W): r/z columns accumulate onto gi, n-gate
+            // columns go to ghn; chunks that straddle a gate boundary take the element path
+            auto merge_chunk = [&](float* g, float* gn, int n0, const float* a, auto width) {
+                constexpr int W = decltype(width)::value;
+                if (n0 + W <= H2) {
+                    if (W == 4) {
+                        float4 v = *reinterpret_cast<float4*>(g + n0);
+                        v.x += a[0]; v.y += a[1]; v.z += a[2]; v.w += a[3];
+                        *reinterpret_cast<float4*>(g + n0) = v;
+                    } else {
+                        float2 v = *reinterpret_cast<float2*>(g + n0);
+                        v.x += a[0]; v.y += a[1];
+                        *reinterpret_cast<float2*>(g + n0) = v;
+                    }
+                } else if (n0 >= H2 && n0 + W <= 3 * H) {
+#pragma unroll
+                    for (int c = 0; c < W; ++c) gn[n0 - H2 + c] = a[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < W; ++c) {
+                        const int n = n0 + c;
+                        if (n < H2) g[n] += a[c];
+                        else if (n < 3 * H) gn[n - H2] = a[c];
+                    }
+                }
+            };
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int b = rbase + 4 * i;
                 float* g = gis + b * ldg;
                 float* gn = ghn + b * KP;
-                const float a10[10] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y, acc[i][2].x,
-                                       acc[i][2].y, acc[i][3].x, acc[i][3].y, acc[i][4].x, acc[i][4].y};
-#pragma unroll
-                for (int c = 0; c < 10; ++c) {
-                    const int n = c < 4 ? cA + c : c < 8 ? cB + (c - 4) : cC + (c - 8);
-                    if (n < H2) g[n] += a10[c];                  // r, z: gi + gh
-                    else if (n < 3 * H) gn[n - H2] = a10[c];     // n gate: keep gh apart
-                }
+                const float aA[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+                const float aB[4] = {acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y};
+                const float aC[2] = {acc[i][4].x, acc[i][4].y};
+                merge_chunk(g, gn, cA, aA, IntC<4>{});
+                merge_chunk(g, gn, cB, aB, IntC<4>{});
+                merge_chunk(g, gn, cC, aC, IntC<2>{});
             }
         }
+#if WG_RC_ALTERNATE
+        if (!handed_over) {  // a warp without a column block still takes part in the hand-over
+            if (grp == 0) group_arrive(3, NT);
+            else if (t + 1 < T) group_arrive(4, NT);
+        }
+#else
+        (void)handed_over;
+#endif
+        WG_TRACE(3);
         group_barrier(1 + grp, NG);
+        WG_TRACE(4);
 
         // ================= gate phase =================
+        // Two passes: first every item's new state is computed into registers (loads and MUFU
+        // chains of different items are independent, so they overlap), only then the stores —
+        // a store to hs in between would order every later shared-memory load behind it.
+        {
+            float hnew[kRcMaxQ];
 #pragma unroll
-        for (int q = 0; q < kRcMaxQ; ++q) {
-            if (item_bj[q] >= 0) {
-                const int b = item_bj[q] >> 16, j = item_bj[q] & 0xffff;
+            for (int q = 0; q < kRcMaxQ; ++q) {
+                const int pk = item_bj[q] >= 0 ? item_bj[q] : (grp * GB) << 16;  // invalid slot: harmless item
+                const int b = pk >> 16, j = pk & 0xffff;
                 const float* g = gis + b * ldg + j;
+#if WG_GATE_EXP == 2
+                const float r = g[0] * 0.25f;
+                const float z = g[H] * 0.25f;
+                const float n = (g[H2] + r * (ghn[b * KP + j] + bns[j])) * 0.25f;
+#else
                 const float r = sigmoid_f(g[0]);
                 const float z = sigmoid_f(g[H]);
                 const float n = tanh_f(g[H2] + r * (ghn[b * KP + j] + bns[j]));
-                const float hold = hs[b * RS + j];
-                const float hnew = (hold - n) * z + n;
-                hs[b * RS + j] = hnew;
-                out[((size_t)(b0 + b) * T + t) * H + j] = hnew;
+#endif
+                hnew[q] = (hs[b * RS + j] - n) * z + n;
+            }
+            float* out_t = out + (size_t)b0 * T * H + (size_t)t * H;
+#pragma unroll
+            for (int q = 0; q < kRcMaxQ; ++q) {
+                if (item_bj[q] >= 0) {
+                    const int b = item_bj[q] >> 16, j = item_bj[q] & 0xffff;
+#if WG_GATE_EXP != 3
+                    hs[b * RS + j] = hnew[q];
+#endif
+#if WG_GATE_EXP != 1
+                    out_t[(size_t)b * T * H + j] = hnew[q];
+#endif
+                }
             }
         }
+        WG_TRACE(5);
         group_barrier(1 + grp, NG);
+        WG_TRACE(6);
         if (t + 1 < T) prefetch_gi(t + 1);  // lands during the next GEMM
+        WG_TRACE(7);
     }
 }
 
