@@ -110,6 +110,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic_bytes(kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu summary
+    (profiles/, same workload); None if no capture is committed."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted(f for f in os.listdir(pdir) if f.endswith("_ncu_summary.json"))
+    except OSError:
+        return None
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    for name in names:  # the last (latest round) wins
+        try:
+            with open(os.path.join(pdir, name)) as f:
+                summ = json.load(f)
+            for k in summ["kernels"]:
+                if kernel_substr in k["kernel"]:
+                    best = (k["dram__bytes_read.sum"] * scale[k["dram__bytes_read.sum.unit"]]
+                            + k["dram__bytes_write.sum"] * scale[k["dram__bytes_write.sum.unit"]])
+        except Exception:
+            continue
+    return best
+
+
 def cpu_port_seq_per_s(sd, adj32, n_seq: int, min_seconds: float, max_reps: int, seed: int = 0):
     """The oracle's torch-CPU port (same library kernels as the reference, batch-generalised) on all
     host threads.  Returns (sequences/s, threads, reps, seconds)."""
@@ -142,10 +165,10 @@ def run_reference(args, rank: int):
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    n_seq = 512  # bounded sample of the 4096-sequence step
+    n_seq = args.ref_seqs  # bounded sample of the 4096-sequence step
     x = torch.rand((n_seq, T, S, F), generator=torch.Generator().manual_seed(0))
     for _ in range(max(1, min(args.warmup, 2))):
-        gcn_gru_forward_torch(adj32, x[:64], sd)
+        gcn_gru_forward_torch(adj32, x[: min(64, n_seq)], sd)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         gcn_gru_forward_torch(adj32, x, sd)
@@ -173,6 +196,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="sequences per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-seqs", type=int, default=512, help="sequences per step of the reference arm's sample")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -214,12 +238,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from windgnn_b200.shard import max_over_ranks as _max_over_ranks
+
     def max_over_ranks(v: float) -> float:
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max_over_ranks(v, dev)
 
     # ---------------- device-resident throughput (`value`) ----------------
     with torch.no_grad():
@@ -318,7 +340,7 @@ def main():
             "bound": "fp32", "kernel": "inproj_kernel (GRU input projection, FFMA GEMM)",
             "achieved": inproj_tflops, "peak": ffma_peak, "unit": "TFLOP/s", "frac": inproj_tflops / ffma_peak,
             "peak_source": "FFMA microbenchmark measured live on this GPU (wg_measure_ffma_tflops)",
-            "peak_nominal": nominal_peak, "traffic": None,
+            "peak_nominal": nominal_peak, "traffic": ncu_traffic_bytes("inproj"), "traffic_unit": "bytes per launch (ncu dram read+write)",
             "algorithmic_flops_per_launch": inproj_flops,
             "kernel_ms": stage_ms,
             "path": {"achieved": path_tflops, "frac_fp32": path_tflops / ffma_peak,
@@ -328,9 +350,9 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             adj_cpu = adj.cpu()
-            v, threads, reps, secs = cpu_port_seq_per_s(sd, adj_cpu, n_seq=1024, min_seconds=10.0, max_reps=20)
+            v, threads, reps, secs = cpu_port_seq_per_s(sd, adj_cpu, n_seq=2048, min_seconds=12.0, max_reps=40)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{reps} x 1024 sequences of the same workload in {secs:.1f} s, torch CPU fp32"}
+                   "sample": f"{reps} x 2048 sequences of the same workload in {secs:.1f} s, torch CPU fp32"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -1,0 +1,87 @@
+"""Host logic of the multi-GPU path, exercised with world_size-2 gloo process groups on CPU."""
+
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+from windgnn_b200.shard import aggregate_throughput, max_over_ranks, shard_range
+
+
+def test_shard_range_covers_batch_exactly():
+    for n in (0, 1, 7, 4096, 1 << 20, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(n, rank, world)
+        spans = [None] * world
+        dist.all_gather_object(spans, (lo, hi))
+        slow = max_over_ranks(0.5 + rank)              # rank r pretends to take 0.5 + r seconds
+        thr = aggregate_throughput(100, 0.5 + rank)
+        # shards of an elementwise-independent op reassemble to the unsharded result
+        x = torch.arange(n, dtype=torch.float32)
+        parts = [None] * world
+        dist.all_gather_object(parts, (x[lo:hi] * 2 + 1).tolist())
+        q.put((rank, spans, slow, thr, sum(parts, [])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_timing_reduction():
+    world, n = 2, 11
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, spans, slow, thr, whole in results:
+        assert spans == [(0, 6), (6, 11)]
+        assert slow == 1.5                              # max over ranks, not the local time
+        assert thr == pytest.approx(2 * 100 / 1.5)      # all ranks' units / slowest rank
+        assert whole == [2.0 * i + 1 for i in range(n)]
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """`bench.py --impl reference` launched like the driver does for N > 1: rank 0 alone works and
+    prints the JSON line, the other rank exits 0 silently."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+           "--ref-seqs", "16"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
