@@ -348,7 +348,7 @@ def main():
                      "frac_hbm": hbm_gbs / hbm_peak, "flop_per_seq": FLOP_PER_SEQ, "bytes_per_seq": BYTES_PER_SEQ},
         }
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
             adj_cpu = adj.cpu()
             v, threads, reps, secs = cpu_port_seq_per_s(sd, adj_cpu, n_seq=2048, min_seconds=12.0, max_reps=40)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
