@@ -219,6 +219,9 @@ def main():
     if world > 1:
         import torch.distributed as dist  # noqa: F811
 
+        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     warmup = max(args.warmup, 3)
