@@ -59,43 +59,69 @@ def load_workload():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: one streaming
+    `nvidia-smi -lms 20` process started ahead of time; `mark_start()` / `mark_stop()` bracket the
+    region and only samples stamped inside it are summarised."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self._stop = threading.Event()
-        self._thread = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                    capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([v.strip() for v in out.splitlines()[0].split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        self.proc = None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.5)  # let it start streaming before the timed region begins
+        except OSError:
+            self.proc = None
         return self
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
+
     def __exit__(self, *a):
-        self._stop.set()
-        self._thread.join(timeout=10)
+        self.rows = []
+        if self.proc is None:
+            return
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=10)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        import datetime
+
+        for line in out.splitlines():
+            parts = [v.strip() for v in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                continue
+            self.rows.append((ts, parts[1:]))
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        lo = (self.t0 or 0) - 0.02
+        hi = (self.t1 or 1e18) + 0.02
+        inside = [r for ts, r in self.rows if lo <= ts <= hi]
+        where = "timed region"
+        if not inside:  # region shorter than the sampling period: fall back to the nearest samples
+            inside = [r for _, r in sorted(self.rows, key=lambda x: abs(x[0] - (self.t0 or 0)))[:3]]
+            where = "nearest to timed region"
+        sm, mx, reasons = [], [], set()
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -107,7 +133,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": where}
 
 
 def ncu_traffic_bytes(kernel_substr: str):
@@ -254,11 +280,13 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as clocks:
             barrier()
+            clocks.mark_start()
             e0.record()
             for _ in range(steps):
                 y = model(adj, x)
             e1.record()
             barrier()
+            clocks.mark_stop()
         ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * Bg * steps / (ms * 1e-3)
     n_chunks = (Bg + 148 * 32 - 1) // (148 * 32)
