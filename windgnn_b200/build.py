@@ -23,7 +23,7 @@ LIB = os.path.join(LIBDIR, "libwindgnn_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 UNITS = [
-    ("abi.cu", []),
+    ("abi.cu", ["-ftz=true"]),  # denormals flushed: single-instruction ex2/rcp in the gate math
     ("graph.cu", ["-fmad=false"]),
 ]
 

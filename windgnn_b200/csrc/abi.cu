@@ -219,26 +219,28 @@ int launch_inproj(const Plan& p, void* ws, long long rows, cudaStream_t st) {
 
 template <int NW, bool WS>
 int launch_recur_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
-    const size_t smem = wg::recur_smem_floats(p.KP, p.NPR, p.GP, WS) * 4;
+    // stage h in shared memory for bulk stores when it fits, else store every step directly
+    int TS = wg::recur_stage_steps(p.H);
+    size_t smem = wg::recur_smem_floats(p.KP, p.NPR, p.GP, WS, p.H, TS) * 4;
+    if (smem > (size_t)wg::kMaxSmemOptin) {
+        TS = 0;
+        smem = wg::recur_smem_floats(p.KP, p.NPR, p.GP, WS) * 4;
+    }
     auto kern = wg::gru_recur_kernel<NW, WS>;
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (Bc + wg::kRcBT - 1) / wg::kRcBT;
     if (grid < 1) return WG_OK;
     kern<<<(unsigned)grid, NW * 32, smem, st>>>(ws_ptr<float>(ws, p.off_gi), ws_ptr<float>(ws, p.off_wht),
                                                ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, p.GP,
-                                               p.KP, p.NPR);
+                                               p.KP, p.NPR, TS);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
 
 template <bool WS>
 int launch_recur_ws(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
-    // warps per 16-sequence group: one per 80-column block (1, 2, 4 or 8; more blocks are looped).
-    // kRcMaxQ = 14 gate items per thread always suffices: 16 H <= 14 * 32 * ceil(3H / 80).
+    // warps per 16-sequence group: one per 80-column block (1, 2, 4 or 8; more blocks are looped)
     const int blocks = p.NPR / wg::kRcCB;
-    if ((wg::kRcBT / 2) * p.H > wg::kRcMaxQ * 32 * 8)
-        return fail(WG_ERR_UNSUPPORTED, "GRU hidden size %d too large for the recurrence kernel (max %d)",
-                    p.H, wg::kRcMaxQ * 32 * 8 / (wg::kRcBT / 2));
     if (blocks <= 1) return launch_recur_t<2, WS>(p, ws, out, Bc, st);
     if (blocks <= 2) return launch_recur_t<4, WS>(p, ws, out, Bc, st);
     if (blocks <= 4) return launch_recur_t<8, WS>(p, ws, out, Bc, st);

@@ -30,13 +30,15 @@ namespace wg {
 
 constexpr int kRcBT = 32;    // sequences per CTA (two groups of 16)
 constexpr int kRcCB = 80;    // gate columns per warp
-constexpr int kRcMaxQ = 14;  // gate items per thread: 16 * H <= kRcMaxQ * 32 * warps_per_group
 
 __host__ __device__ inline int recur_np(int G) { return round_up(G, kRcCB); }
 // hidden-state rows: KP floats padded so that four consecutive rows start in distinct bank groups
 __host__ __device__ inline int recur_hs_stride(int KP) { return ((KP / 4) & 1) ? KP : KP + 4; }
-__host__ __device__ inline size_t recur_smem_floats(int KP, int NP, int GP, bool w_smem) {
-    size_t n = 0;
+// timesteps staged in shared memory per bulk store of h: the smallest count that makes one
+// sequence's staged block (TS * H floats) a multiple of 16 bytes
+__host__ __device__ inline int recur_stage_steps(int H) { return (H % 4 == 0) ? 1 : (H % 2 == 0) ? 2 : 4; }
+__host__ __device__ inline size_t recur_smem_floats(int KP, int NP, int GP, bool w_smem, int H = 0, int TS = 0) {
+    size_t n = (size_t)round_up(kRcBT * TS * H, 4);  // staging of h for the bulk stores (TS = 0: none)
     if (w_smem) n += (size_t)KP * NP;
     n += (size_t)kRcBT * recur_hs_stride(KP);  // hs
     n += (size_t)kRcBT * GP;                   // gi tile (r,z columns become gi + gh)
@@ -61,6 +63,9 @@ struct IntC { static constexpr int value = N; };
 #ifndef WG_GATE_EXP
 #define WG_GATE_EXP 0
 #endif
+#ifndef WG_GEMM_EXP
+#define WG_GEMM_EXP 0
+#endif
 #ifdef WG_RC_TRACE
 // debug build only: per-phase clock stamps of CTA 0 (8 stamps per step per group)
 __device__ long long g_rc_trace[2 * 8 * 256];
@@ -84,7 +89,7 @@ template <int NWARPS, bool W_SMEM>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
     gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ WhT,
                      const float* __restrict__ bhn, float* __restrict__ out, long long B, int T, int H,
-                     int ldg, int KP, int NP) {
+                     int ldg, int KP, int NP, int TS) {
     constexpr int NT = NWARPS * 32;
     constexpr int WG = NWARPS / 2;   // warps per group
     constexpr int NG = WG * 32;      // threads per group
@@ -96,6 +101,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
     float* gis = hs + kRcBT * RS;          // [32][ldg]
     float* ghn = gis + kRcBT * ldg;        // [32][KP]
     float* bns = ghn + kRcBT * KP;         // [KP]
+    float* stage = bns + KP;               // [32][TS][H] h of the last TS steps (TS > 0)
+    // bulk (TMA) stores of h need 16-byte aligned, 16-byte-multiple spans per sequence
+    const bool bulk_ok = TS > 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (((long long)T * H) & 3) == 0 &&
+                         ((TS * H) & 3) == 0;
     const float* Wsrc = W_SMEM ? Ws : WhT;
 
     const int tid = threadIdx.x;
@@ -118,22 +127,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
     for (int e = tid; e < kRcBT * KP; e += NT) ghn[e] = 0.0f;
     for (int e = tid; e < KP; e += NT) bns[e] = e < H ? __ldg(bhn + e) : 0.0f;
 
-    // ---- gate-phase items of this thread inside its group: (b, j) packed as b<<16 | j ----
-    const int n_items = GB * H;
-    int item_bj[kRcMaxQ];
-#pragma unroll
-    for (int q = 0; q < kRcMaxQ; ++q) {
-        const int item = gtid + q * NG;
-        int b = -1, j = 0;
-        if (item < n_items) {
-            b = item / H;
-            j = item - b * H;
-            b += grp * GB;
-            if (b0 + b >= B) b = -1;  // ragged last CTA
-        }
-        item_bj[q] = b < 0 ? -1 : ((b << 16) | j);
-    }
-
     // ---- GEMM-phase coordinates ----
     const int ln = lane & 7;   // column slot within the warp's 80 columns
     const int bg = lane >> 3;  // row group
@@ -144,16 +137,18 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
     auto prefetch_gi = [&](int t) {
         for (int cb = gwarp; cb < n_cb; cb += WG) {
             const int cA = cb * kRcCB + ln * 4, cB = cA + 32, cC = cb * kRcCB + 64 + ln * 2;
+            const float* src = GI + ((size_t)(b0 + rbase) * T + t) * ldg;   // row rbase; rows are 4*T*ldg apart
+            float* dst = gis + rbase * ldg;
+            const size_t src_step = (size_t)4 * T * ldg;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int b = rbase + 4 * i;
-                if (b0 + b < B) {
-                    const float* src = GI + ((size_t)(b0 + b) * T + t) * ldg;
-                    float* dst = gis + b * ldg;
+                if (b0 + rbase + 4 * i < B) {
                     if (cA < ldg) cp_async16(dst + cA, src + cA, true);
                     if (cB < ldg) cp_async16(dst + cB, src + cB, true);
                     if (cC < ldg) cp_async8(dst + cC, src + cC);
                 }
+                src += src_step;
+                dst += 4 * ldg;
             }
         }
         cp_async_commit();
@@ -232,6 +227,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
                 RcFrag fa, fb;
                 load_frag(fa);
                 int k4 = 4;
+#if WG_GEMM_EXP == 1
+                load_frag(fb);   // experiment: no loads inside the loop (wrong results, timing only)
+#pragma unroll 1
+                for (; k4 + 4 < KP; k4 += 8) {
+                    mma_frag(fa);
+                    mma_frag(fb);
+                }
+#else
 #pragma unroll 1
                 for (; k4 + 4 < KP; k4 += 8) {
                     load_frag(fb);
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
                     load_frag(fa);
                     mma_frag(fb);
                 }
+#endif
                 if (k4 < KP) {   // even number of fragments: one more pair
                     load_frag(fb);
                     mma_frag(fa);
@@ -256,44 +260,43 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
 #endif
             WG_TRACE(2);
             cp_async_wait<0>();  // this thread's chunks of gi(t) have landed
-            // merge one aligned chunk of W columns [n0, n0 + W): r/z columns accumulate onto gi, n-gate
-            // columns go to ghn; chunks that straddle a gate boundary take the element path
-            auto merge_chunk = [&](float* g, float* gn, int n0, const float* a, auto width) {
+            // merge: r/z columns accumulate onto gi (vector read-modify-write), n-gate columns go to
+            // ghn; a chunk that straddles a gate boundary (or the padding) takes the element path.
+            // The class of a chunk is the same for the thread's four rows.
+            auto merge_chunk = [&](int n0, auto width, int p0) {
                 constexpr int W = decltype(width)::value;
                 if (n0 + W <= H2) {
-                    if (W == 4) {
-                        float4 v = *reinterpret_cast<float4*>(g + n0);
-                        v.x += a[0]; v.y += a[1]; v.z += a[2]; v.w += a[3];
-                        *reinterpret_cast<float4*>(g + n0) = v;
-                    } else {
-                        float2 v = *reinterpret_cast<float2*>(g + n0);
-                        v.x += a[0]; v.y += a[1];
-                        *reinterpret_cast<float2*>(g + n0) = v;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float* g = gis + (rbase + 4 * i) * ldg + n0;
+                        if (W == 4) {
+                            float4 v = *reinterpret_cast<float4*>(g);
+                            v.x += acc[i][p0].x; v.y += acc[i][p0].y; v.z += acc[i][p0 + 1].x; v.w += acc[i][p0 + 1].y;
+                            *reinterpret_cast<float4*>(g) = v;
+                        } else {
+                            float2 v = *reinterpret_cast<float2*>(g);
+                            v.x += acc[i][p0].x; v.y += acc[i][p0].y;
+                            *reinterpret_cast<float2*>(g) = v;
+                        }
                     }
-                } else if (n0 >= H2 && n0 + W <= 3 * H) {
+                } else if (n0 < 3 * H) {
 #pragma unroll
-                    for (int c = 0; c < W; ++c) gn[n0 - H2 + c] = a[c];
-                } else {
+                    for (int i = 0; i < 4; ++i) {
+                        float* g = gis + (rbase + 4 * i) * ldg;
+                        float* gn = ghn + (rbase + 4 * i) * KP;
 #pragma unroll
-                    for (int c = 0; c < W; ++c) {
-                        const int n = n0 + c;
-                        if (n < H2) g[n] += a[c];
-                        else if (n < 3 * H) gn[n - H2] = a[c];
+                        for (int c = 0; c < W; ++c) {
+                            const int n = n0 + c;
+                            const float a = (c & 1) ? acc[i][p0 + (c >> 1)].y : acc[i][p0 + (c >> 1)].x;
+                            if (n < H2) g[n] += a;
+                            else if (n < 3 * H) gn[n - H2] = a;
+                        }
                     }
                 }
             };
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int b = rbase + 4 * i;
-                float* g = gis + b * ldg;
-                float* gn = ghn + b * KP;
-                const float aA[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
-                const float aB[4] = {acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y};
-                const float aC[2] = {acc[i][4].x, acc[i][4].y};
-                merge_chunk(g, gn, cA, aA, IntC<4>{});
-                merge_chunk(g, gn, cB, aB, IntC<4>{});
-                merge_chunk(g, gn, cC, aC, IntC<2>{});
-            }
+            merge_chunk(cA, IntC<4>{}, 0);
+            merge_chunk(cB, IntC<4>{}, 2);
+            merge_chunk(cC, IntC<2>{}, 4);
         }
 #if WG_RC_ALTERNATE
         if (!handed_over) {  // a warp without a column block still takes part in the hand-over
@@ -304,51 +307,70 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
         (void)handed_over;
 #endif
         WG_TRACE(3);
+        if (bulk_ok && gtid < GB) bulk_wait_read();  // the previous bulk store has read its staging rows
         group_barrier(1 + grp, NG);
         WG_TRACE(4);
 
         // ================= gate phase =================
-        // Two passes: first every item's new state is computed into registers (loads and MUFU
-        // chains of different items are independent, so they overlap), only then the stores —
-        // a store to hs in between would order every later shared-memory load behind it.
-        {
-            float hnew[kRcMaxQ];
+        // A thread owns hidden unit(s) j and walks the group's 16 sequences: every address is a
+        // running pointer (no index arithmetic), lanes lie along j (conflict-free shared accesses),
+        // and four sequences are in flight at once so their MUFU chains overlap.
+        for (int j = gtid; j < H; j += NG) {
+            const float bn = bns[j];
+            // distinct buffers: __restrict__ lets the loads of later sequences pass earlier stores
+            const float* __restrict__ g = gis + (grp * GB) * ldg + j;
+            const float* __restrict__ gn = ghn + (grp * GB) * KP + j;
+            float* __restrict__ hp = hs + (grp * GB) * RS + j;
+            float* __restrict__ sp = stage + (grp * GB) * TS * H + (TS > 0 ? (t % TS) * H : 0) + j;
+            float* __restrict__ op = out + ((size_t)(b0 + grp * GB) * T + t) * H + j;
+            const size_t o_step = (size_t)T * H;
+            const int s_step = TS * H;
+            // pass 1: all 16 new states into registers (no store in between, so the loads and MUFU
+            // chains of different sequences overlap); pass 2: the stores
+            float hnew[GB];
 #pragma unroll
-            for (int q = 0; q < kRcMaxQ; ++q) {
-                const int pk = item_bj[q] >= 0 ? item_bj[q] : (grp * GB) << 16;  // invalid slot: harmless item
-                const int b = pk >> 16, j = pk & 0xffff;
-                const float* g = gis + b * ldg + j;
-#if WG_GATE_EXP == 2
-                const float r = g[0] * 0.25f;
-                const float z = g[H] * 0.25f;
-                const float n = (g[H2] + r * (ghn[b * KP + j] + bns[j])) * 0.25f;
-#else
-                const float r = sigmoid_f(g[0]);
-                const float z = sigmoid_f(g[H]);
-                const float n = tanh_f(g[H2] + r * (ghn[b * KP + j] + bns[j]));
-#endif
-                hnew[q] = (hs[b * RS + j] - n) * z + n;
+            for (int bl = 0; bl < GB; ++bl) {
+                const float r = sigmoid_f(g[bl * ldg]);
+                const float z = sigmoid_f(g[bl * ldg + H]);
+                const float n = tanh_f(g[bl * ldg + H2] + r * (gn[bl * KP] + bn));
+                hnew[bl] = (hp[bl * RS] - n) * z + n;
             }
-            float* out_t = out + (size_t)b0 * T * H + (size_t)t * H;
 #pragma unroll
-            for (int q = 0; q < kRcMaxQ; ++q) {
-                if (item_bj[q] >= 0) {
-                    const int b = item_bj[q] >> 16, j = item_bj[q] & 0xffff;
-#if WG_GATE_EXP != 3
-                    hs[b * RS + j] = hnew[q];
-#endif
-#if WG_GATE_EXP != 1
-                    out_t[(size_t)b * T * H + j] = hnew[q];
-#endif
-                }
+            for (int bl = 0; bl < GB; ++bl) {
+                hp[bl * RS] = hnew[bl];
+                if (TS > 0) sp[bl * s_step] = hnew[bl];
+                else if (b0 + grp * GB + bl < B) op[bl * o_step] = hnew[bl];
             }
         }
+        if (TS > 0) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // staged h -> async proxy
         WG_TRACE(5);
         group_barrier(1 + grp, NG);
         WG_TRACE(6);
+        if (TS > 0 && ((t % TS) == TS - 1 || t == T - 1)) {
+            // flush the staged steps t0 .. t of this group's 16 sequences to out[b][t0 .. t][:]
+            const int t0 = t - (t % TS), nst = t - t0 + 1;
+            if (bulk_ok && nst == TS) {
+                if (gtid < GB) {
+                    const int b = grp * GB + gtid;
+                    if (b0 + b < B) {
+                        bulk_s2g(out + ((size_t)(b0 + b) * T + t0) * H, stage + b * TS * H, (unsigned)(TS * H * 4));
+                        bulk_commit();
+                    }
+                }
+            } else {
+                const int per_seq = nst * H;
+                for (int e = gtid; e < GB * per_seq; e += NG) {
+                    const int bl = e / per_seq, r = e - bl * per_seq;
+                    const int b = grp * GB + bl;
+                    if (b0 + b < B) out[((size_t)(b0 + b) * T + t0) * H + r] = stage[b * TS * H + r];
+                }
+                group_barrier(1 + grp, NG);  // the staging rows are free again
+            }
+        }
         if (t + 1 < T) prefetch_gi(t + 1);  // lands during the next GEMM
         WG_TRACE(7);
     }
+    if (bulk_ok && gtid < GB) bulk_wait_read();  // shared memory must outlive the last bulk store's reads
 }
 
 }  // namespace wg

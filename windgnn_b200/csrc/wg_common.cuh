@@ -62,6 +62,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// shared -> global bulk copy (TMA store path), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+
 // ---- activations ------------------------------------------------------------------------
 // ex2.approx-based; absolute error ~1e-7, far below the 1e-5 normalised parity bar
 // (tanh.approx.f32 would not be: 2^-11 relative).
