@@ -142,6 +142,27 @@ int wg_build_graph_f64(const double* xy, double* adj_f64, float* adj_f32, int S,
 int wg_synthetic_coordinates_f64(double* latlon, int S, uint64_t seed, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * step4 windows — replaces `__create_sequences(data, seq_length)`
+ * (src/step4_sequence_preparer.py:7-27) for the numeric block of the pivoted table.
+ *   table  [Ttot, S, F] fp32 device: columns 2:15 of the reference's [time, station, 15] table
+ *          (feature f = column f + 2; label column 13 = feature 11)
+ *   perm   int64 [N] device, window order (the reference shuffles, :23-26); NULL = identity
+ *   x      [N, L, S, F]        x[n] = table[perm[n]*L : (perm[n]+1)*L]                  (:13)
+ *   y      [N, L, horizons*S]  y[n, l, k*S+s] = table[perm[n]*L + l + 1 + k, s, label_f] (:14-18)
+ *   Either of x / y may be NULL.  N*L + horizons <= Ttot is required (the reference would build
+ *   ragged label arrays otherwise); wg_num_windows gives the largest such N.
+ *
+ * De-normalised last-step predictions — replaces `outputs * (wind_max - wind_min) + wind_min`
+ * (src/main.py:103) restricted to the last timestep the evaluation reads (main.py:116,131,146):
+ *   out [B, T, H] -> pred [B, H], fp32 arithmetic with NumPy's two roundings.
+ * ---------------------------------------------------------------------------------- */
+int64_t wg_num_windows(int64_t Ttot, int L, int horizons);
+int wg_make_windows_f32(const float* table, const int64_t* perm, float* x, float* y, int64_t Ttot, int S,
+                        int F, int L, int label_f, int horizons, int64_t N, int device, void* stream);
+int wg_denorm_last_step_f32(const float* out, float* pred, int64_t B, int T, int H, double vmin,
+                            double vmax, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement helper: sustained FP32 FFMA throughput of this device in TFLOP/s (2 flops per
  * FFMA), measured with CUDA events over `iters` launches of a register-resident FFMA loop.
  * Used by bench.py as the FP32 roofline denominator.  Returns < 0 on error.

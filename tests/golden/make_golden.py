@@ -56,7 +56,25 @@ def ref_forward(model, adj, x):
         return torch.stack([model(adj, x[b : b + 1]) for b in range(x.shape[0])])
 
 
+def make_windows_golden():
+    """``windows.npz``: the reference's own ``__create_sequences`` (step4:7-27) on a small seeded
+    table, plus the shuffle indices it drew (recovered by re-seeding NumPy's global RNG)."""
+    import step4_sequence_preparer as step4
+
+    create = step4.__dict__["__create_sequences"]
+    rng = np.random.default_rng(99)
+    Ttot, S, L = 3 * 24 + 5, 4, 24
+    table = rng.random((Ttot, S, 15)).astype(np.float32).astype(np.float64)
+    np.random.seed(4321)
+    x, y = create(table, L)
+    np.random.seed(4321)
+    idx = np.arange(x.shape[0])
+    np.random.shuffle(idx)
+    np.savez_compressed(os.path.join(HERE, "windows.npz"), table=table, x=x, y=y, indices=idx, seq_length=L)
+
+
 def main():
+    make_windows_golden()
     torch.manual_seed(0)
     np.random.seed(0)
     torch.set_num_threads(1)  # deterministic summation order in MKL

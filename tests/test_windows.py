@@ -1,0 +1,88 @@
+"""step4 window extraction and the de-normalised last-step slice: oracle pinned to the reference's
+own ``__create_sequences`` (CPU), CUDA path bit-exact against the oracle (GPU)."""
+
+import numpy as np
+import pytest
+import torch
+
+import windgnn_b200
+from conftest import golden
+from oracle import create_sequences, denorm_last_step
+from windgnn_b200 import _lib
+
+DEV = "cuda:0"
+
+
+def test_oracle_matches_reference_create_sequences():
+    g = golden("windows.npz")
+    x, y = create_sequences(g["table"], int(g["seq_length"]), g["indices"])
+    assert x.shape == g["x"].shape == (3, 24, 4, 13) and y.shape == g["y"].shape == (3, 24, 12)
+    assert np.array_equal(x, g["x"]) and np.array_equal(y, g["y"])
+    # label layout: y[n, l, k*S + s] = wind speed (column 13) k+1 rows later
+    n = int(g["indices"][0])
+    assert y[0, 5, 2 * 4 + 1] == g["table"][n * 24 + 5 + 3, 1, 13]
+
+
+def test_num_windows_host_logic():
+    assert windgnn_b200.num_windows(168 * 5 + 3) == 5
+    assert windgnn_b200.num_windows(168 * 5 + 2) == 4     # labels of the 5th window would be ragged
+    assert windgnn_b200.num_windows(100) == 0
+    assert windgnn_b200.num_windows(77, 24, 3) == 3
+    lib = _lib.load()
+    assert lib.wg_make_windows_f32(None, None, None, None, 10, 2, 13, 24, 11, 3, 1, 0, None) == _lib.WG_ERR_BAD_ARG
+    assert lib.wg_denorm_last_step_f32(None, None, 0, 168, 102, 0.0, 1.0, 0, None) == _lib.WG_OK
+
+
+@pytest.mark.gpu
+def test_windows_bit_exact_vs_reference_golden():
+    g = golden("windows.npz")
+    L = int(g["seq_length"])
+    table = torch.from_numpy(g["table"][:, :, 2:15].astype(np.float32)).to(DEV)
+    perm = torch.from_numpy(g["indices"].astype(np.int64)).to(DEV)
+    x, y = windgnn_b200.create_sequences(table, L, perm=perm)
+    assert torch.equal(x.cpu(), torch.from_numpy(g["x"].astype(np.float32)))
+    assert torch.equal(y.cpu(), torch.from_numpy(g["y"].astype(np.float32)))
+    # chronological order: x is a zero-copy view of the table
+    x0, y0 = windgnn_b200.create_sequences(table, L)
+    assert x0.data_ptr() == table.data_ptr() and x0.shape == (3, L, 4, 13)
+    xo, yo = create_sequences(g["table"], L)
+    assert torch.equal(x0.cpu(), torch.from_numpy(xo.astype(np.float32)))
+    assert torch.equal(y0.cpu(), torch.from_numpy(yo.astype(np.float32)))
+
+
+@pytest.mark.gpu
+def test_windows_full_size_properties():
+    """The real dataset's shape: 3 years of hourly rows, 34 stations (26,304 x 34 x 13)."""
+    Ttot, S = 26304, 34
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    table = torch.rand((Ttot, S, 13), generator=gen, device=DEV)
+    N = windgnn_b200.num_windows(Ttot)
+    assert N == Ttot // 168                                   # 156 full windows, 96 spare rows
+    perm = torch.randperm(N, device=DEV, generator=gen)
+    x, y = windgnn_b200.create_sequences(table, perm=perm)
+    assert x.shape == (N, 168, S, 13) and y.shape == (N, 168, 3 * S)
+    flat = table.view(-1, S, 13)
+    n = 17
+    w = int(perm[n])
+    assert torch.equal(x[n], flat[w * 168:(w + 1) * 168])
+    for k in range(3):
+        assert torch.equal(y[n, :, k * S:(k + 1) * S], flat[w * 168 + 1 + k:(w + 1) * 168 + 1 + k, :, 11])
+    # a permutation only reorders windows
+    x2, y2 = windgnn_b200.create_sequences(table)
+    assert torch.equal(x2[perm], x) and torch.equal(y2[perm], y)
+    with pytest.raises(_lib.WindGNNError):
+        windgnn_b200.create_sequences(table[: 168 * 3 + 2], perm=torch.arange(3, device=DEV))
+
+
+@pytest.mark.gpu
+def test_denormalise_last_step_bit_exact():
+    rng = np.random.default_rng(3)
+    out = (rng.random((37, 9, 21), dtype=np.float32) * 2 - 1).astype(np.float32)
+    wmin, wmax = 0.0, 83.6                                     # km/h range of the kind step1:56-58 returns
+    pred = windgnn_b200.denormalise_last_step(torch.from_numpy(out).to(DEV), wmin, wmax).cpu().numpy()
+    assert np.array_equal(pred, denorm_last_step(out, wmin, wmax))
+    wmin, wmax = 1.25, 97.30000000000001
+    pred = windgnn_b200.denormalise_last_step(torch.from_numpy(out).to(DEV), wmin, wmax).cpu().numpy()
+    assert np.array_equal(pred, denorm_last_step(out, wmin, wmax))
+    one = windgnn_b200.denormalise_last_step(torch.from_numpy(out[0]).to(DEV), wmin, wmax)   # [T, H] like the reference
+    assert one.shape == (1, 21)

@@ -21,7 +21,12 @@ from .graph import (  # noqa: F401
     synthetic_coordinates,
 )
 
+from .sequences import create_sequences, denormalise_last_step, num_windows  # noqa: F401
+
 __all__ = [
+    "create_sequences",
+    "denormalise_last_step",
+    "num_windows",
     "GCN_GRU",
     "GraphConvLayer",
     "build_graph",

@@ -47,6 +47,9 @@ _SIGNATURES = {
     "wg_build_graph_workspace_bytes": (c_size_t, [c_int, c_int]),
     "wg_build_graph_f64": (c_int, [_P, _P, _P, c_int, c_int, _P, c_size_t, c_int, _P]),
     "wg_synthetic_coordinates_f64": (c_int, [_P, c_int, c_uint64, c_int, _P]),
+    "wg_num_windows": (c_int64, [c_int64, c_int, c_int]),
+    "wg_make_windows_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, _P]),
+    "wg_denorm_last_step_f32": (c_int, [_P, _P, c_int64, c_int, c_int, c_double, c_double, c_int, _P]),
     "wg_measure_ffma_tflops": (c_double, [c_int, c_int]),
 }
 

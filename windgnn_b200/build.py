@@ -25,6 +25,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("abi.cu", ["-ftz=true"]),  # denormals flushed: single-instruction ex2/rcp in the gate math
     ("graph.cu", ["-fmad=false"]),
+    ("windows.cu", []),
 ]
 
 
