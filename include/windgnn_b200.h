@@ -71,6 +71,20 @@ int wg_gcn_gru_forward_f32(const float* adj, const float* x, const float* w1, co
                            int F_in, int F_hid, int F_out, int H, int64_t chunk, void* workspace,
                            size_t workspace_bytes, int device, void* stream);
 
+/* Same forward with the adjacency given as CSR (int32 row pointers [S+1], column indices and fp32
+ * values [nnz], device pointers): the scaled-shape path — thousands of stations with a few
+ * neighbours each, GCN hidden width up to 512 (F_in, F_out <= 16).  Used for BASELINE.json's
+ * 4096-station kNN configuration; the dense entry point above is the tuned path for the shipped
+ * 7- / 34-station models. */
+size_t wg_gcn_gru_csr_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
+                                      int64_t chunk);
+int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                               const float* x, const float* w1, const float* b1, const float* w2,
+                               const float* b2, const float* w_ih, const float* w_hh, const float* b_ih,
+                               const float* b_hh, float* out, int64_t B, int T, int S, int F_in,
+                               int F_hid, int F_out, int H, int64_t chunk, void* workspace,
+                               size_t workspace_bytes, int device, void* stream);
+
 /* Same computation with HOST buffers for x (pinned for full overlap) and out: the batch is
  * streamed through the device in `chunk`-sized pieces, H2D copy / compute / D2H copy of
  * consecutive pieces overlapped on internal streams.  Parameters and adj are device

@@ -216,8 +216,57 @@ def test_stage_entry_points_compose(full34):
     assert torch.equal(out, y[:B])
 
 
+def _scaled_model(S, Fh, H, seed):
+    """GCN_GRU(13, Fh, 13, 13*S, H) with the weight scale SURVEY.md 8(d) prescribes for wide layers
+    (unscaled randn saturates the GRU)."""
+    torch.manual_seed(seed)
+    m = windgnn_b200.GCN_GRU(13, Fh, 13, 13 * S, H)
+    with torch.no_grad():
+        m.conv1.weight.mul_(0.05)
+        m.conv2.weight.mul_(0.05)
+    return m
+
+
+@pytest.mark.parametrize("S,Fh,H,B,T,k", [(300, 128, 128, 3, 6, 8), (96, 40, 30, 5, 4, 3), (150, 13, 36, 2, 5, 8)])
+def test_sparse_graph_path_vs_oracle(S, Fh, H, B, T, k):
+    """CSR adjacency path (large kNN graph, wide GCN hidden layer) against the oracle."""
+    from oracle import knn_graph_f64, synthetic_coordinates
+
+    adj = knn_graph_f64(synthetic_coordinates(S, seed=S), k).astype(np.float32)
+    m = _scaled_model(S, Fh, H, seed=S + B)
+    sd = {kk: v.detach().clone() for kk, v in m.state_dict().items()}
+    x = np.random.default_rng(S).random((B, T, S, 13), dtype=np.float32)
+    ref = gcn_gru_forward(adj, x, sd, dtype=np.float32)
+    m = m.to(DEV)
+    m.DENSE_MAX_STATIONS = 64                                          # force the CSR path for S = 96 too
+    with torch.no_grad():
+        y = m(torch.from_numpy(adj).to(DEV), torch.from_numpy(x).to(DEV)).reshape(B, T, H).cpu().numpy()
+    assert normalised_max_error(y, ref) <= TOL
+
+
+def test_config4_4096_station_knn_graph():
+    """BASELINE.json configs[3]: synthetic 4096-station kNN(k=8) graph, GCN hidden 128, 24-step window
+    (GRU hidden 128 — SURVEY.md 8(d) variant C), graph built on the GPU, forward against the oracle."""
+    S, Fh, H, B, T = 4096, 128, 128, 2, 24
+    latlon = windgnn_b200.synthetic_coordinates(S, seed=0, device=DEV).cpu().numpy()
+    adj = windgnn_b200.knn_graph_from_latlon(latlon, k=8, device=DEV)
+    assert int((adj != 0).sum(1).max()) < 64
+    m = _scaled_model(S, Fh, H, seed=4)
+    sd = {kk: v.detach().clone() for kk, v in m.state_dict().items()}
+    x = np.random.default_rng(0).random((B, T, S, 13), dtype=np.float32)
+    ref = gcn_gru_forward(adj.cpu().numpy(), x, sd, dtype=np.float32)
+    with torch.no_grad():
+        y = m.to(DEV)(adj, torch.from_numpy(x).to(DEV)).cpu().numpy()
+    assert y.shape == (B, T, H)
+    assert normalised_max_error(y, ref) <= TOL
+    # shard / chunk invariance holds on this path too
+    with torch.no_grad():
+        y1 = m(adj, torch.from_numpy(x[1:]).to(DEV)).cpu().numpy()
+    assert np.array_equal(y1, y[1])
+
+
 def test_errors_are_reported_not_thrown_across_the_abi():
-    m = windgnn_b200.GCN_GRU(20, 20, 13, 13 * 4, 12).to(DEV)          # feature width 20 > 16: unsupported
+    m = windgnn_b200.GCN_GRU(20, 20, 13, 13 * 4, 12).to(DEV)          # F_in 20 > 16: unsupported on both paths
     with pytest.raises(_lib.WindGNNError) as ei:
         m(torch.eye(4, device=DEV), torch.zeros((2, 3, 4, 20), device=DEV))
     assert ei.value.code == _lib.WG_ERR_UNSUPPORTED

@@ -37,6 +37,8 @@ _SIGNATURES = {
     "wg_last_error": (c_char_p, []),
     "wg_gcn_gru_workspace_bytes": (c_size_t, [c_int64, *_DIMS, c_int64]),
     "wg_gcn_gru_forward_f32": (c_int, [_P] * 11 + [c_int64, *_DIMS, c_int64, _P, c_size_t, c_int, _P]),
+    "wg_gcn_gru_csr_workspace_bytes": (c_size_t, [c_int64, *_DIMS, c_int64]),
+    "wg_gcn_gru_forward_csr_f32": (c_int, [_P] * 13 + [c_int64, *_DIMS, c_int64, _P, c_size_t, c_int, _P]),
     "wg_gcn_gru_host_workspace_bytes": (c_size_t, [c_int64, *_DIMS, c_int64]),
     "wg_gcn_gru_forward_host_f32": (c_int, [_P] * 11 + [c_int64, *_DIMS, c_int64, _P, c_size_t, c_int]),
     "wg_gcn_layer_f32": (c_int, [_P] * 5 + [c_int64, c_int, c_int, c_int, c_int, _P]),

@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "gcn.cuh"
+#include "gcn_sparse.cuh"
 #include "inproj.cuh"
 #include "recur.cuh"
 #include "wg_common.cuh"
@@ -59,23 +60,30 @@ struct Plan {
     int GP;        // leading dim of GI: G rounded up to 4
     int KP;        // K of the recurrent GEMM: H rounded up to 4
     int NPR;       // columns of packed w_hh^T: G rounded up to 80 (one warp's column block)
-    size_t off_wp, off_bias, off_wht, off_bhn, off_u, off_gi, total;
+    bool sparse;   // CSR graph path: adds the Z scratch of the sparse GCN kernels
+    size_t off_wp, off_bias, off_wht, off_bhn, off_u, off_gi, off_z, total;
 };
 
-long long default_chunk(long long B) {
-    const long long one_wave = (long long)wg::kNumSMs * wg::kRcBT;  // 4736 sequences
-    return B < one_wave ? (B < 1 ? 1 : B) : one_wave;
+long long default_chunk(long long B, size_t bytes_per_seq) {
+    long long c = (long long)wg::kNumSMs * wg::kRcBT;  // 4736 sequences: one wave of the recurrence
+    // keep the per-chunk scratch under ~6 GB for the scaled shapes (whole 32-sequence CTAs)
+    const size_t cap = (size_t)6 << 30;
+    if ((size_t)c * bytes_per_seq > cap) {
+        c = (long long)(cap / bytes_per_seq) / wg::kRcBT * wg::kRcBT;
+        if (c < wg::kRcBT) c = wg::kRcBT;
+    }
+    return B < c ? (B < 1 ? 1 : B) : c;
 }
 
-int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H, long long chunk) {
+int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H, long long chunk,
+              bool sparse = false) {
     if (B < 0 || T <= 0 || S <= 0 || Fi <= 0 || Fh <= 0 || Fo <= 0 || H <= 0 || chunk < 0)
         return fail(WG_ERR_BAD_ARG, "non-positive dimension (B=%lld T=%d S=%d F=%d/%d/%d H=%d chunk=%lld)",
                     B, T, S, Fi, Fh, Fo, H, chunk);
     if ((long long)S * Fo > (1 << 20) || H > (1 << 15))
         return fail(WG_ERR_UNSUPPORTED, "dimension too large (S*F_out=%lld, H=%d)", (long long)S * Fo, H);
     p.T = T; p.S = S; p.Fi = Fi; p.Fh = Fh; p.Fo = Fo; p.H = H;
-    p.chunk = chunk > 0 ? chunk : default_chunk(B);
-    if (p.chunk > B && B > 0) p.chunk = B;
+    p.sparse = sparse;
     p.I = S * Fo;
     p.G = 3 * H;
     p.IP = wg::round_up(p.I, wg::kIpBK);
@@ -83,6 +91,11 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     p.GP = wg::round_up(p.G, 4);
     p.KP = wg::round_up(H, 4);
     p.NPR = wg::recur_np(p.G);
+    {
+        const size_t per_seq = (size_t)T * ((size_t)p.IP + p.GP + (sparse ? (size_t)S * Fo : 0)) * 4;
+        p.chunk = chunk > 0 ? chunk : default_chunk(B, per_seq);
+        if (p.chunk > B && B > 0) p.chunk = B;
+    }
     size_t o = 0;
     p.off_wp = o;   o = align_up(o + (size_t)p.NPB * p.IP * 4);
     p.off_bias = o; o = align_up(o + (size_t)p.NPB * 4);
@@ -92,6 +105,7 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     const size_t rows_tiled = (rows + wg::kUTileRows - 1) / wg::kUTileRows * wg::kUTileRows;
     p.off_u = o;    o = align_up(o + rows_tiled * p.IP * 4);  // K-major 128-row tiles
     p.off_gi = o;   o = align_up(o + rows * p.GP * 4);
+    p.off_z = o;    if (sparse) o = align_up(o + rows * (size_t)S * Fo * 4);
     p.total = o;
     return WG_OK;
 }
@@ -202,6 +216,39 @@ int launch_gcn(const float* X, const float* adj, const float* W1, const float* b
     return fail(WG_ERR_UNSUPPORTED, "GCN feature width %d > 16 is not built into the dense kernel", fmax);
 }
 
+struct Csr {
+    const int* rowptr;
+    const int* colidx;
+    const float* vals;
+};
+
+int launch_gcn_sparse(const Plan& p, void* ws, const Csr& g, const float* x, const float* w1, const float* b1,
+                      const float* w2, const float* b2, long long rows, cudaStream_t st) {
+    if (p.Fi > wg::kSpF || p.Fo > wg::kSpF)
+        return fail(WG_ERR_UNSUPPORTED, "sparse GCN: F_in / F_out must be <= %d (got %d / %d)", wg::kSpF, p.Fi, p.Fo);
+    const size_t smem = ((size_t)2 * p.Fh * wg::kSpF + p.Fh) * 4;
+    if (smem > (size_t)wg::kMaxSmemOptin)
+        return fail(WG_ERR_UNSUPPORTED, "sparse GCN: hidden width %d too large", p.Fh);
+    const long long tiles = (rows + wg::kSpThreads - 1) / wg::kSpThreads;
+    if (tiles < 1) return WG_OK;
+    // split the stations so that the grid fills the machine a few times over
+    int chunks = (int)((4LL * wg::kNumSMs * 4 + tiles - 1) / tiles);
+    if (chunks < 1) chunks = 1;
+    if (chunks > p.S) chunks = p.S;
+    const int s_chunk = (p.S + chunks - 1) / chunks;
+    const dim3 grid((unsigned)tiles, (unsigned)((p.S + s_chunk - 1) / s_chunk));
+    WG_CUDA(cudaFuncSetAttribute(wg::gcn_sparse_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wg::gcn_sparse_l1_kernel<<<grid, wg::kSpThreads, smem, st>>>(x, g.rowptr, g.colidx, g.vals, w1, b1, w2,
+                                                                ws_ptr<float>(ws, p.off_z), rows, p.S, p.Fi, p.Fh,
+                                                                p.Fo, s_chunk);
+    WG_CUDA(cudaGetLastError());
+    wg::gcn_sparse_l2_kernel<<<grid, wg::kSpThreads, 0, st>>>(ws_ptr<float>(ws, p.off_z), g.rowptr, g.colidx, g.vals,
+                                                             b2, ws_ptr<float>(ws, p.off_u), rows, p.S, p.Fo, p.IP,
+                                                             s_chunk);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
 int launch_inproj(const Plan& p, void* ws, long long rows, cudaStream_t st) {
     const long long m_tiles = (rows + wg::kIpBM - 1) / wg::kIpBM;
     const int n_tiles = p.NPB / wg::kIpBN;
@@ -270,6 +317,16 @@ int run_chunk(const Plan& p, void* ws, const float* adj, const float* x, const f
     const long long rows = Bc * p.T;
     int rc = launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_u), rows, p.S, p.Fi, p.Fh,
                                  p.Fo, p.IP, st);
+    if (rc) return rc;
+    rc = launch_inproj(p, ws, rows, st);
+    if (rc) return rc;
+    return launch_recur(p, ws, out, Bc, st);
+}
+
+int run_chunk_csr(const Plan& p, void* ws, const Csr& g, const float* x, const float* w1, const float* b1,
+                  const float* w2, const float* b2, float* out, long long Bc, cudaStream_t st) {
+    const long long rows = Bc * p.T;
+    int rc = launch_gcn_sparse(p, ws, g, x, w1, b1, w2, b2, rows, st);
     if (rc) return rc;
     rc = launch_inproj(p, ws, rows, st);
     if (rc) return rc;
@@ -388,6 +445,41 @@ int wg_gcn_gru_forward_f32(const float* adj, const float* x, const float* w1, co
         const long long Bc = (B - b0) < p.chunk ? (B - b0) : p.chunk;
         rc = run_chunk(p, workspace, adj, x + (size_t)b0 * x_seq, w1, b1, w2, b2, out + (size_t)b0 * o_seq,
                        Bc, st);
+        if (rc) return rc;
+    }
+    return WG_OK;
+}
+
+size_t wg_gcn_gru_csr_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
+                                      int64_t chunk) {
+    Plan p;
+    if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, true)) return 0;
+    return p.total;
+}
+
+int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals, const float* x,
+                               const float* w1, const float* b1, const float* w2, const float* b2,
+                               const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                               float* out, int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
+                               int64_t chunk, void* workspace, size_t workspace_bytes, int device,
+                               void* stream) {
+    Plan p;
+    int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, true);
+    if (rc) return rc;
+    if (B == 0) return WG_OK;
+    if (any_null({rowptr, colidx, vals, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, out}))
+        return fail(WG_ERR_BAD_ARG, "null pointer argument");
+    if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = launch_pack(p, workspace, w_ih, w_hh, b_ih, b_hh, st))) return rc;
+    const Csr csr{rowptr, colidx, vals};
+    const size_t x_seq = (size_t)T * S * F_in, o_seq = (size_t)T * H;
+    for (long long b0 = 0; b0 < B; b0 += p.chunk) {
+        const long long Bc = (B - b0) < p.chunk ? (B - b0) : p.chunk;
+        rc = run_chunk_csr(p, workspace, csr, x + (size_t)b0 * x_seq, w1, b1, w2, b2, out + (size_t)b0 * o_seq,
+                           Bc, st);
         if (rc) return rc;
     }
     return WG_OK;

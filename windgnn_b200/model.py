@@ -39,12 +39,15 @@ class GCN_GRU(nn.Module):
     state_dict keys (``gru.weight_ih_l0`` ...) match the reference's.
     """
 
+    DENSE_MAX_STATIONS = 128  # above this the adjacency is handed to the library as CSR
+
     def __init__(self, input_dim, hidden_dim, output_dim, gru_input, gru_hidden_dim):
         super().__init__()
         self.conv1 = GraphConvLayer(input_dim, hidden_dim)
         self.conv2 = GraphConvLayer(hidden_dim, output_dim)
         self.gru = nn.GRU(gru_input, gru_hidden_dim, batch_first=True)
         self.chunk = 0  # sequences per internal pass; 0 = library default
+        self._csr_cache = None  # (key, (rowptr, colidx, vals)) of the last large adjacency seen
 
     def forward(self, adj_matrix, attr_matrix):
         if attr_matrix.dim() != 4:
@@ -52,12 +55,19 @@ class GCN_GRU(nn.Module):
             raise RuntimeError(
                 f"attr_matrix must be [B, T, S, F_in], got {tuple(attr_matrix.shape)}"
             )
-        out = ops.gcn_gru_forward(
-            adj_matrix, attr_matrix,
+        params = (
             self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
             self.gru.weight_ih_l0, self.gru.weight_hh_l0, self.gru.bias_ih_l0, self.gru.bias_hh_l0,
-            self.chunk,
         )
+        widths = (self.conv1.weight.shape[0], self.conv1.weight.shape[1], self.conv2.weight.shape[1])
+        if adj_matrix.shape[0] > self.DENSE_MAX_STATIONS or max(widths) > 16:
+            # scaled shapes (thousands of stations, wide hidden layer): CSR adjacency path
+            key = (adj_matrix.data_ptr(), adj_matrix._version, tuple(adj_matrix.shape))
+            if self._csr_cache is None or self._csr_cache[0] != key:
+                self._csr_cache = (key, ops.dense_to_csr(adj_matrix))
+            out = ops.gcn_gru_forward_csr(*self._csr_cache[1], attr_matrix, *params, self.chunk)
+        else:
+            out = ops.gcn_gru_forward(adj_matrix, attr_matrix, *params, self.chunk)
         return out.squeeze(0)  # step6:26 — a no-op unless B == 1
 
     @torch.no_grad()

@@ -125,6 +125,78 @@ def _(adj, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, chunk=0):
     return x.new_empty((x.shape[0], x.shape[1], w_hh.shape[1]))
 
 
+@torch.library.custom_op("windgnn::gcn_gru_forward_csr", mutates_args=())
+def gcn_gru_forward_csr(
+    rowptr: torch.Tensor,
+    colidx: torch.Tensor,
+    vals: torch.Tensor,
+    x: torch.Tensor,
+    w1: torch.Tensor,
+    b1: torch.Tensor,
+    w2: torch.Tensor,
+    b2: torch.Tensor,
+    w_ih: torch.Tensor,
+    w_hh: torch.Tensor,
+    b_ih: torch.Tensor,
+    b_hh: torch.Tensor,
+    chunk: int = 0,
+) -> torch.Tensor:
+    """The same forward with the adjacency in CSR form (int32 ``rowptr [S+1]``, ``colidx [nnz]``,
+    fp32 ``vals [nnz]``): the large-sparse-graph path (thousands of stations, wide GCN hidden layer)."""
+    lib = _lib.load()
+    x = _require_cuda_f32("attr_matrix", x)
+    dev = x.device
+    w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, vals = (
+        _require_cuda_f32(n, t, dev)
+        for n, t in (
+            ("conv1.weight", w1), ("conv1.bias", b1), ("conv2.weight", w2), ("conv2.bias", b2),
+            ("gru.weight_ih_l0", w_ih), ("gru.weight_hh_l0", w_hh), ("gru.bias_ih_l0", b_ih),
+            ("gru.bias_hh_l0", b_hh), ("adjacency values", vals),
+        )
+    )
+    if x.dim() != 4:
+        raise RuntimeError(f"attr_matrix must be [B, T, S, F_in], got {tuple(x.shape)}")
+    S = x.shape[2]
+    for n, t in (("rowptr", rowptr), ("colidx", colidx)):
+        if not t.is_cuda or t.dtype != torch.int32 or t.device != dev:
+            raise RuntimeError(f"windgnn_b200: {n} must be a CUDA int32 tensor on {dev}")
+    rowptr, colidx = rowptr.contiguous(), colidx.contiguous()
+    if rowptr.numel() != S + 1 or colidx.numel() != vals.numel():
+        raise RuntimeError("CSR arrays do not match the number of stations")
+    adj_shape = torch.empty((S, S), device="meta")
+    B, T, S, F_in, F_hid, F_out, H = _dims(adj_shape, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh)
+    out = torch.empty((B, T, H), dtype=torch.float32, device=dev)
+    if B == 0 or T == 0:
+        return out
+    nbytes = lib.wg_gcn_gru_csr_workspace_bytes(B, T, S, F_in, F_hid, F_out, H, chunk)
+    if nbytes == 0:
+        raise _lib.WindGNNError(_lib.WG_ERR_BAD_ARG, _lib.last_error())
+    ws = _workspace(dev, nbytes)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(
+        lib.wg_gcn_gru_forward_csr_f32(
+            rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(), x.data_ptr(), w1.data_ptr(), b1.data_ptr(),
+            w2.data_ptr(), b2.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
+            out.data_ptr(), B, T, S, F_in, F_hid, F_out, H, chunk, ws.data_ptr(), ws.numel(), dev.index or 0, stream,
+        )
+    )
+    return out
+
+
+@gcn_gru_forward_csr.register_fake
+def _(rowptr, colidx, vals, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, chunk=0):
+    return x.new_empty((x.shape[0], x.shape[1], w_hh.shape[1]))
+
+
+def dense_to_csr(adj: torch.Tensor):
+    """(rowptr int32 [S+1], colidx int32 [nnz], vals fp32 [nnz]) of a dense CUDA adjacency, columns
+    ascending within a row.  Index plumbing only (torch); the arithmetic stays in the library."""
+    adj = _require_cuda_f32("adj_matrix", adj)
+    csr = adj.to_sparse_csr()
+    return (csr.crow_indices().to(torch.int32).contiguous(), csr.col_indices().to(torch.int32).contiguous(),
+            csr.values().contiguous())
+
+
 @torch.library.custom_op("windgnn::gcn_layer", mutates_args=())
 def gcn_layer(adj: torch.Tensor, attr: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """``relu((adj @ attr) @ weight + bias)`` for ``attr [..., S, F_in]``."""
