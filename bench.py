@@ -222,6 +222,8 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="sequences per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3"],
+                    help="fp32: every contraction as FP32 FMA; tf32x3: GRU input projection on tcgen05 (3xTF32)")
     ap.add_argument("--ref-seqs", type=int, default=512, help="sequences per step of the reference arm's sample")
     args = ap.parse_args()
 
@@ -258,6 +260,8 @@ def main():
     model = windgnn_b200.GCN_GRU(F, F, F, I, H)
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).eval()
+    model.precision = args.precision
+    flags = model._flags()
     adj = windgnn_b200.build_graph_from_latlon(latlon, device=dev, dtype=torch.float32)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.rand((Bg, T, S, F), generator=gen, device=dev)  # 1.22 GB at B=4096: larger than the 126 MB L2
@@ -297,7 +301,7 @@ def main():
     stage_ms = {}
     if rank == 0:
         Bc = min(Bg, 148 * 32)
-        nbytes = lib.wg_gcn_gru_workspace_bytes(Bc, *dims, Bc)
+        nbytes = lib.wg_gcn_gru_workspace_bytes(Bc, *dims, Bc, flags)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out = torch.empty((Bc, T, H), device=dev)
         p = [t.detach().contiguous() for t in (
@@ -306,10 +310,10 @@ def main():
         st = torch.cuda.current_stream(dev).cuda_stream
         xs = x[:Bc]
         calls = {
-            "pack": lambda: lib.wg_stage_pack_f32(*(t.data_ptr() for t in p[4:]), *dims, Bc, ws.data_ptr(), nbytes, local_rank, st),
-            "gcn": lambda: lib.wg_stage_gcn_f32(adj.data_ptr(), xs.data_ptr(), *(t.data_ptr() for t in p[:4]), Bc, *dims, Bc, ws.data_ptr(), nbytes, local_rank, st),
-            "inproj": lambda: lib.wg_stage_inproj_f32(Bc, *dims, Bc, ws.data_ptr(), nbytes, local_rank, st),
-            "recur": lambda: lib.wg_stage_recur_f32(out.data_ptr(), Bc, *dims, Bc, ws.data_ptr(), nbytes, local_rank, st),
+            "pack": lambda: lib.wg_stage_pack_f32(*(t.data_ptr() for t in p[4:]), *dims, Bc, flags, ws.data_ptr(), nbytes, local_rank, st),
+            "gcn": lambda: lib.wg_stage_gcn_f32(adj.data_ptr(), xs.data_ptr(), *(t.data_ptr() for t in p[:4]), Bc, *dims, Bc, flags, ws.data_ptr(), nbytes, local_rank, st),
+            "inproj": lambda: lib.wg_stage_inproj_f32(Bc, *dims, Bc, flags, ws.data_ptr(), nbytes, local_rank, st),
+            "recur": lambda: lib.wg_stage_recur_f32(out.data_ptr(), Bc, *dims, Bc, flags, ws.data_ptr(), nbytes, local_rank, st),
         }
         for name in ("pack", "gcn", "inproj", "recur"):
             for _ in range(3):
@@ -368,7 +372,9 @@ def main():
         path_tflops = FLOP_PER_SEQ * Bg * steps / (ms * 1e-3) / 1e12  # per GPU
         hbm_gbs = BYTES_PER_SEQ * Bg * steps / (ms * 1e-3) / 1e9     # per GPU, algorithmic
         roofline = {
-            "bound": "fp32", "kernel": "inproj_kernel (GRU input projection, FFMA GEMM)",
+            "bound": "fp32", "kernel": ("inproj_kernel (GRU input projection, FFMA2 GEMM)" if flags == 0 else
+                                        "inproj_tc_kernel (GRU input projection, tcgen05 3xTF32; fraction is of the "
+                                        "FP32 FMA peak the FP32 path is bound by)"),
             "achieved": inproj_tflops, "peak": ffma_peak, "unit": "TFLOP/s", "frac": inproj_tflops / ffma_peak,
             "peak_source": "FFMA microbenchmark measured live on this GPU (wg_measure_ffma_tflops)",
             "peak_nominal": nominal_peak, "traffic": ncu_traffic_bytes("inproj"), "traffic_unit": "bytes per launch (ncu dram read+write)",
@@ -387,8 +393,10 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "34-station GCN-GRU forward (wind_gnn_34.pth), T=168, batch 4096 per GPU "
+            "dtype": "f32" if flags == 0 else "f32 (input projection: 3xTF32 tensor cores, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"precision": args.precision,
+                       "workload": "34-station GCN-GRU forward (wind_gnn_34.pth), T=168, batch 4096 per GPU "
                                    "(BASELINE.json configs[1])", "S": S, "T": T, "batch_per_gpu": Bg,
                        "global_batch": Bg * world, "parallelism": f"sequence-sharded x{world}, no collective",
                        "l2_policy": "inputs (1.22 GB per step) larger than L2",

@@ -27,7 +27,10 @@
 extern "C" {
 #endif
 
-#define WG_ABI_VERSION 1
+#define WG_ABI_VERSION 2
+
+/* `flags` of the GCN-GRU entry points */
+#define WG_FLAG_TENSOR_CORES 1 /* input projection on tcgen05 with error-compensated TF32 (3xTF32) */
 
 enum {
     WG_OK = 0,
@@ -61,14 +64,19 @@ const char* wg_last_error(void);
  * sequences are independent (h0 = 0 for each).
  *
  * `chunk` = sequences processed per internal pass (bounds the workspace); 0 = default.
+ * `flags`: 0 = every contraction as FP32 FMA (the reference's arithmetic, different summation
+ *   order).  WG_FLAG_TENSOR_CORES = the GRU input projection (65 % of the FLOPs) runs on the
+ *   tcgen05 tensor cores as three TF32 products per term (hi*hi + hi*lo + lo*hi, fp32
+ *   accumulate); its error against fp64 is the same size as the FP32 path's and it is held to
+ *   the same 1e-5 parity bar.  Needs 3H <= 512.  The workspace must be sized with the same flags.
  * ---------------------------------------------------------------------------------- */
 size_t wg_gcn_gru_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
-                                  int64_t chunk);
+                                  int64_t chunk, int flags);
 
 int wg_gcn_gru_forward_f32(const float* adj, const float* x, const float* w1, const float* b1,
                            const float* w2, const float* b2, const float* w_ih, const float* w_hh,
                            const float* b_ih, const float* b_hh, float* out, int64_t B, int T, int S,
-                           int F_in, int F_hid, int F_out, int H, int64_t chunk, void* workspace,
+                           int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags, void* workspace,
                            size_t workspace_bytes, int device, void* stream);
 
 /* Same forward with the adjacency given as CSR (int32 row pointers [S+1], column indices and fp32
@@ -92,13 +100,13 @@ int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, con
  * until `out_host` is complete.  Replaces the per-window loop of src/main.py:101-103
  * (`model(adj, batch_x)` followed by `.cpu()`). */
 size_t wg_gcn_gru_host_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
-                                       int64_t chunk);
+                                       int64_t chunk, int flags);
 
 int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const float* w1,
                                 const float* b1, const float* w2, const float* b2,
                                 const float* w_ih, const float* w_hh, const float* b_ih,
                                 const float* b_hh, float* out_host, int64_t B, int T, int S,
-                                int F_in, int F_hid, int F_out, int H, int64_t chunk,
+                                int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags,
                                 void* workspace, size_t workspace_bytes, int device);
 
 /* ------------------------------------------------------------------------------------
@@ -113,7 +121,7 @@ int wg_gcn_layer_f32(const float* adj, const float* attr, const float* weight, c
 /* ------------------------------------------------------------------------------------
  * Stage entry points (the three kernels wg_gcn_gru_forward_f32 chains).  Exposed so the
  * benchmark can time, and the tests can check, each kernel alone.  `workspace` must have
- * been sized by wg_gcn_gru_workspace_bytes for the same dims and must already hold the
+ * been sized by wg_gcn_gru_workspace_bytes for the same dims and flags and must already hold the
  * packed parameters (wg_stage_pack_f32) before stages 2 and 3.
  *   stage_pack  : re-lay w_ih / w_hh / biases for the kernels
  *   stage_gcn   : x [Bc,T,S,F_in] -> U [Bc*T, IP]        (two GCN layers, fused)
@@ -122,17 +130,17 @@ int wg_gcn_layer_f32(const float* adj, const float* attr, const float* weight, c
  * Bc must be <= the chunk the workspace was sized for.
  * ---------------------------------------------------------------------------------- */
 int wg_stage_pack_f32(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                      int T, int S, int F_in, int F_hid, int F_out, int H, int64_t chunk,
+                      int T, int S, int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags,
                       void* workspace, size_t workspace_bytes, int device, void* stream);
 int wg_stage_gcn_f32(const float* adj, const float* x, const float* w1, const float* b1,
                      const float* w2, const float* b2, int64_t Bc, int T, int S, int F_in, int F_hid,
-                     int F_out, int H, int64_t chunk, void* workspace, size_t workspace_bytes,
+                     int F_out, int H, int64_t chunk, int flags, void* workspace, size_t workspace_bytes,
                      int device, void* stream);
 int wg_stage_inproj_f32(int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H,
-                        int64_t chunk, void* workspace, size_t workspace_bytes, int device,
+                        int64_t chunk, int flags, void* workspace, size_t workspace_bytes, int device,
                         void* stream);
 int wg_stage_recur_f32(float* out, int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H,
-                       int64_t chunk, void* workspace, size_t workspace_bytes, int device,
+                       int64_t chunk, int flags, void* workspace, size_t workspace_bytes, int device,
                        void* stream);
 
 /* ------------------------------------------------------------------------------------

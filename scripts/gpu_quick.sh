@@ -2,7 +2,7 @@
 # quick iteration loop: smoke parity + stage timings
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | python -c "
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e $BENCH_ARGS 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     l=l.strip()

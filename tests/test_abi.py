@@ -25,7 +25,7 @@ def test_library_builds_and_loads():
     path = build.build()
     assert os.path.exists(path)
     lib = _lib.load()
-    assert lib.wg_abi_version() == _lib.ABI_VERSION == 1
+    assert lib.wg_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_every_declared_symbol_is_exported():
@@ -41,17 +41,20 @@ def test_every_declared_symbol_is_exported():
 def test_workspace_planning():
     lib = _lib.load()
     dims34 = (168, 34, 13, 13, 13, 102)
-    one = lib.wg_gcn_gru_workspace_bytes(1, *dims34, 0)
-    big = lib.wg_gcn_gru_workspace_bytes(4096, *dims34, 0)
+    one = lib.wg_gcn_gru_workspace_bytes(1, *dims34, 0, 0)
+    big = lib.wg_gcn_gru_workspace_bytes(4096, *dims34, 0, 0)
     assert 0 < one < big
     # scratch per sequence = T * (IP + GP) * 4 with IP = 448, GP = 308 (U is kept in 128-row tiles)
-    per_seq = (big - lib.wg_gcn_gru_workspace_bytes(4096 - 128, *dims34, 0)) / 128
+    per_seq = (big - lib.wg_gcn_gru_workspace_bytes(4096 - 128, *dims34, 0, 0)) / 128
     assert per_seq == pytest.approx(168 * (448 + 308) * 4, rel=1e-3)
     # the default chunk caps the scratch: 1M sequences need no more than one wave's worth
-    assert lib.wg_gcn_gru_workspace_bytes(1 << 20, *dims34, 0) == lib.wg_gcn_gru_workspace_bytes(148 * 32, *dims34, 0)
-    assert lib.wg_gcn_gru_workspace_bytes(1 << 20, *dims34, 1024) < big
-    assert lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 0) > big
-    assert lib.wg_gcn_gru_workspace_bytes(8, 0, 34, 13, 13, 13, 102, 0) == 0  # T = 0 is invalid
+    assert lib.wg_gcn_gru_workspace_bytes(1 << 20, *dims34, 0, 0) == lib.wg_gcn_gru_workspace_bytes(148 * 32, *dims34, 0, 0)
+    assert lib.wg_gcn_gru_workspace_bytes(1 << 20, *dims34, 1024, 0) < big
+    assert lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 0, 0) > big
+    # the tensor-core path keeps U and w_ih as hi + lo parts: more scratch; unknown flags are rejected
+    assert lib.wg_gcn_gru_workspace_bytes(4096, *dims34, 0, _lib.FLAG_TENSOR_CORES) > big
+    assert lib.wg_gcn_gru_workspace_bytes(4096, *dims34, 0, 8) == 0
+    assert lib.wg_gcn_gru_workspace_bytes(8, 0, 34, 13, 13, 13, 102, 0, 0) == 0  # T = 0 is invalid
     assert "non-positive" in _lib.last_error()
     assert lib.wg_build_graph_workspace_bytes(34, 0) >= 34 * 34 * 8
     assert lib.wg_build_graph_workspace_bytes(4096, 8) > lib.wg_build_graph_workspace_bytes(4096, 0)
@@ -60,12 +63,12 @@ def test_workspace_planning():
 def test_argument_validation_happens_before_cuda():
     lib = _lib.load()
     dims = (4, 7, 13, 13, 13, 21)
-    rc = lib.wg_gcn_gru_forward_f32(*([None] * 11), -1, *dims, 0, None, 0, 0, None)
+    rc = lib.wg_gcn_gru_forward_f32(*([None] * 11), -1, *dims, 0, 0, None, 0, 0, None)
     assert rc == _lib.WG_ERR_BAD_ARG
-    rc = lib.wg_gcn_gru_forward_f32(*([None] * 11), 2, *dims, 0, None, 0, 0, None)
+    rc = lib.wg_gcn_gru_forward_f32(*([None] * 11), 2, *dims, 0, 0, None, 0, 0, None)
     assert rc == _lib.WG_ERR_BAD_ARG and "null" in _lib.last_error()
     # B == 0 is a valid no-op
-    assert lib.wg_gcn_gru_forward_f32(*([None] * 11), 0, *dims, 0, None, 0, 0, None) == _lib.WG_OK
+    assert lib.wg_gcn_gru_forward_f32(*([None] * 11), 0, *dims, 0, 0, None, 0, 0, None) == _lib.WG_OK
     rc = lib.wg_gcn_layer_f32(None, None, None, None, None, 3, 7, 13, 13, 0, None)
     assert rc == _lib.WG_ERR_BAD_ARG
     with pytest.raises(_lib.WindGNNError):
@@ -74,7 +77,7 @@ def test_argument_validation_happens_before_cuda():
     buf = ctypes.create_string_buffer(1024)
     addr = (ctypes.addressof(buf) + 255) // 256 * 256
     fake = ctypes.c_void_p(8)  # non-null, never dereferenced: validation fails first
-    rc = lib.wg_gcn_gru_forward_f32(*([fake] * 11), 2, *dims, 0, ctypes.c_void_p(addr), 16, 0, None)
+    rc = lib.wg_gcn_gru_forward_f32(*([fake] * 11), 2, *dims, 0, 0, ctypes.c_void_p(addr), 16, 0, None)
     assert rc == _lib.WG_ERR_WORKSPACE and "too small" in _lib.last_error()
-    rc = lib.wg_gcn_gru_forward_f32(*([fake] * 11), 2, *dims, 0, ctypes.c_void_p(addr + 4), 1 << 30, 0, None)
+    rc = lib.wg_gcn_gru_forward_f32(*([fake] * 11), 2, *dims, 0, 0, ctypes.c_void_p(addr + 4), 1 << 30, 0, None)
     assert rc == _lib.WG_ERR_WORKSPACE and "aligned" in _lib.last_error()

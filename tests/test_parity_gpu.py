@@ -199,7 +199,7 @@ def test_stage_entry_points_compose(full34):
     model, adj, x, y = full34
     lib = _lib.load()
     B, dims = 256, (168, 34, 13, 13, 13, 102)
-    nbytes = lib.wg_gcn_gru_workspace_bytes(B, *dims, B)
+    nbytes = lib.wg_gcn_gru_workspace_bytes(B, *dims, B, 0)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
     out = torch.empty((B, 168, 102), device=DEV)
     p = [t.detach().contiguous() for t in (
@@ -207,13 +207,65 @@ def test_stage_entry_points_compose(full34):
         model.gru.weight_ih_l0, model.gru.weight_hh_l0, model.gru.bias_ih_l0, model.gru.bias_hh_l0)]
     st = torch.cuda.current_stream().cuda_stream
     xs = x[:B].contiguous()
-    _lib.check(lib.wg_stage_pack_f32(*(t.data_ptr() for t in p[4:]), *dims, B, ws.data_ptr(), nbytes, 0, st))
-    _lib.check(lib.wg_stage_gcn_f32(adj.data_ptr(), xs.data_ptr(), *(t.data_ptr() for t in p[:4]), B, *dims, B,
+    _lib.check(lib.wg_stage_pack_f32(*(t.data_ptr() for t in p[4:]), *dims, B, 0, ws.data_ptr(), nbytes, 0, st))
+    _lib.check(lib.wg_stage_gcn_f32(adj.data_ptr(), xs.data_ptr(), *(t.data_ptr() for t in p[:4]), B, *dims, B, 0,
                                     ws.data_ptr(), nbytes, 0, st))
-    _lib.check(lib.wg_stage_inproj_f32(B, *dims, B, ws.data_ptr(), nbytes, 0, st))
-    _lib.check(lib.wg_stage_recur_f32(out.data_ptr(), B, *dims, B, ws.data_ptr(), nbytes, 0, st))
+    _lib.check(lib.wg_stage_inproj_f32(B, *dims, B, 0, ws.data_ptr(), nbytes, 0, st))
+    _lib.check(lib.wg_stage_recur_f32(out.data_ptr(), B, *dims, B, 0, ws.data_ptr(), nbytes, 0, st))
     torch.cuda.synchronize()
     assert torch.equal(out, y[:B])
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core path: GRU input projection on tcgen05 with error-compensated TF32 (3xTF32).
+# Stated tolerance: the SAME 1e-5 normalised bar as the FP32 path (three TF32 products per term
+# reproduce fp32 products to ~2^-21, fp32 accumulate).
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S", [7, 34])
+def test_tensor_core_path_matches_reference_golden(S):
+    g = golden(f"fwd_{S}.npz")
+    model = _model(S)
+    model.precision = "tf32x3"
+    adj = torch.from_numpy(_adj(S)).to(DEV)
+    with torch.no_grad():
+        y = model(adj, torch.from_numpy(g["x"]).to(DEV)).cpu().numpy()
+    assert np.isfinite(y).all()
+    assert normalised_max_error(y, g["y_ref_f32"]) <= TOL
+    assert normalised_max_error(y, g["y_ref_f64"]) <= TOL
+
+
+def test_tensor_core_path_full_size(full34):
+    model, adj, x, y = full34
+    model.precision = "tf32x3"
+    try:
+        with torch.no_grad():
+            yt = model(adj, x)
+            yt2 = model(adj, x[1000:1300])
+    finally:
+        model.precision = "fp32"
+    torch.cuda.synchronize()
+    # against the FP32-FMA path on all 4096 sequences, and shard invariance of the tensor path itself
+    err = float((yt - y).abs().max() / y.abs().max())
+    assert err <= TOL, err
+    assert torch.equal(yt2, yt[1000:1300])
+    idx = [0, 127, 128, 4095]
+    ref = gcn_gru_forward(adj.cpu().numpy(), x[idx].cpu().numpy(), load_checkpoint(34))
+    assert normalised_max_error(yt[idx].cpu().numpy(), ref) <= TOL
+
+
+@pytest.mark.parametrize("S,H,B,T", [(3, 9, 33, 7), (12, 36, 70, 11), (20, 50, 31, 6), (40, 150, 9, 5)])
+def test_tensor_core_path_ragged_shapes(S, H, B, T):
+    m = _random_model(S, seed=S * 7 + B, H=H)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    rng = np.random.default_rng(B + 1)
+    adj = (rng.random((S, S), dtype=np.float32) / S).astype(np.float32)
+    x = rng.random((B, T, S, 13), dtype=np.float32)
+    ref = gcn_gru_forward(adj, x, sd, dtype=np.float32)
+    m = m.to(DEV)
+    m.precision = "tf32x3"
+    with torch.no_grad():
+        y = m(torch.from_numpy(adj).to(DEV), torch.from_numpy(x).to(DEV)).reshape(B, T, H).cpu().numpy()
+    assert normalised_max_error(y, ref) <= TOL
 
 
 def _scaled_model(S, Fh, H, seed):

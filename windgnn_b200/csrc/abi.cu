@@ -10,6 +10,7 @@
 #include "gcn.cuh"
 #include "gcn_sparse.cuh"
 #include "inproj.cuh"
+#include "inproj_tc.cuh"
 #include "recur.cuh"
 #include "wg_common.cuh"
 
@@ -61,6 +62,9 @@ struct Plan {
     int KP;        // K of the recurrent GEMM: H rounded up to 4
     int NPR;       // columns of packed w_hh^T: G rounded up to 80 (one warp's column block)
     bool sparse;   // CSR graph path: adds the Z scratch of the sparse GCN kernels
+    bool tc;       // tensor-core (3xTF32 tcgen05) input projection: U and w_ih kept as hi + lo
+    wg::TcShape tcs;
+    size_t off_u_lo, off_wp_lo;
     size_t off_wp, off_bias, off_wht, off_bhn, off_u, off_gi, off_z, total;
 };
 
@@ -76,7 +80,7 @@ long long default_chunk(long long B, size_t bytes_per_seq) {
 }
 
 int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H, long long chunk,
-              bool sparse = false) {
+              bool sparse = false, int flags = 0) {
     if (B < 0 || T <= 0 || S <= 0 || Fi <= 0 || Fh <= 0 || Fo <= 0 || H <= 0 || chunk < 0)
         return fail(WG_ERR_BAD_ARG, "non-positive dimension (B=%lld T=%d S=%d F=%d/%d/%d H=%d chunk=%lld)",
                     B, T, S, Fi, Fh, Fo, H, chunk);
@@ -84,6 +88,7 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
         return fail(WG_ERR_UNSUPPORTED, "dimension too large (S*F_out=%lld, H=%d)", (long long)S * Fo, H);
     p.T = T; p.S = S; p.Fi = Fi; p.Fh = Fh; p.Fo = Fo; p.H = H;
     p.sparse = sparse;
+    if (flags & ~WG_FLAG_TENSOR_CORES) return fail(WG_ERR_BAD_ARG, "unknown flags 0x%x", flags);
     p.I = S * Fo;
     p.G = 3 * H;
     p.IP = wg::round_up(p.I, wg::kIpBK);
@@ -91,19 +96,27 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     p.GP = wg::round_up(p.G, 4);
     p.KP = wg::round_up(H, 4);
     p.NPR = wg::recur_np(p.G);
+    // tensor-core projection: only on the dense small-graph path and when the gate width fits TMEM
+    p.tcs = wg::tc_shape(p.G);
+    p.tc = (flags & WG_FLAG_TENSOR_CORES) != 0 && !sparse;
+    if (p.tc && !p.tcs.ok)
+        return fail(WG_ERR_UNSUPPORTED, "tensor-core projection: unsupported gate width 3H = %d", p.G);
     {
-        const size_t per_seq = (size_t)T * ((size_t)p.IP + p.GP + (sparse ? (size_t)S * Fo : 0)) * 4;
+        const size_t per_seq = (size_t)T * ((size_t)p.IP * (p.tc ? 2 : 1) + p.GP + (sparse ? (size_t)S * Fo : 0)) * 4;
         p.chunk = chunk > 0 ? chunk : default_chunk(B, per_seq);
         if (p.chunk > B && B > 0) p.chunk = B;
     }
     size_t o = 0;
-    p.off_wp = o;   o = align_up(o + (size_t)p.NPB * p.IP * 4);
-    p.off_bias = o; o = align_up(o + (size_t)p.NPB * 4);
+    const int wrows = p.tc ? (p.tcs.NP > p.NPB ? p.tcs.NP : p.NPB) : p.NPB;
+    p.off_wp = o;   o = align_up(o + (size_t)wrows * p.IP * 4);
+    p.off_wp_lo = o; if (p.tc) o = align_up(o + (size_t)wrows * p.IP * 4);
+    p.off_bias = o; o = align_up(o + (size_t)(wrows > 512 ? wrows : 512) * 4);
     p.off_wht = o;  o = align_up(o + (size_t)p.KP * p.NPR * 4);
     p.off_bhn = o;  o = align_up(o + (size_t)p.KP * 4);
     const size_t rows = (size_t)p.chunk * T;
     const size_t rows_tiled = (rows + wg::kUTileRows - 1) / wg::kUTileRows * wg::kUTileRows;
     p.off_u = o;    o = align_up(o + rows_tiled * p.IP * 4);  // K-major 128-row tiles
+    p.off_u_lo = o; if (p.tc) o = align_up(o + rows_tiled * p.IP * 4);
     p.off_gi = o;   o = align_up(o + rows * p.GP * 4);
     p.off_z = o;    if (sparse) o = align_up(o + rows * (size_t)S * Fo * 4);
     p.total = o;
@@ -125,28 +138,45 @@ T* ws_ptr(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>
 // ---------------------------------------------------------------------------------------------
 // parameter packing (tiny; runs every call so the library stays stateless)
 // ---------------------------------------------------------------------------------------------
+// tc_np > 0: w_ih goes out as TF32 hi / lo parts in the UMMA K-major layout [k / 4][tc_np][4]
 __global__ void pack_params_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                    const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                                   float* __restrict__ wp, float* __restrict__ bias,
+                                   float* __restrict__ wp, float* __restrict__ wp_lo, float* __restrict__ bias,
                                    float* __restrict__ wht, float* __restrict__ bhn, int I, int H, int IP,
-                                   int NPB, int KP, int NPR) {
+                                   int NPB, int KP, int NPR, int tc_np, int tc_ne, int n_bias) {
     const int G = 3 * H;
-    const long long n_wp = (long long)NPB * IP;
+    const long long n_wp = tc_np > 0 ? (long long)tc_np * IP : (long long)NPB * IP;
     const long long n_wht = (long long)KP * NPR;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (long long e = t0; e < n_wp; e += stride) {
-        // destination layout [n / 64][k][n % 64] (K-major 64-column tiles, see inproj.cuh)
-        const int nl = (int)(e % wg::kIpBN);
-        const long long r = e / wg::kIpBN;
-        const int k = (int)(r % IP), n = (int)(r / IP) * wg::kIpBN + nl;
-        wp[e] = (n < G && k < I) ? w_ih[(size_t)n * I + k] : 0.0f;
+        if (tc_np > 0) {
+            // destination layout [n / tc_ne][k / 4][n % tc_ne][4] (one contiguous image per column slice)
+            const int j = (int)(e & 3);
+            long long r = e >> 2;
+            const int nl = (int)(r % tc_ne);
+            r /= tc_ne;
+            const int kc = (int)(r % (IP >> 2)), nt = (int)(r / (IP >> 2));
+            const int n = nt * tc_ne + nl, k = kc * 4 + j;
+            const float v = (n < G && k < I) ? w_ih[(size_t)n * I + k] : 0.0f;
+            uint32_t t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+            const float hi = __uint_as_float(t);
+            wp[e] = hi;
+            wp_lo[e] = v - hi;
+        } else {
+            // destination layout [n / 64][k][n % 64] (K-major 64-column tiles, see inproj.cuh)
+            const int nl = (int)(e % wg::kIpBN);
+            const long long r = e / wg::kIpBN;
+            const int k = (int)(r % IP), n = (int)(r / IP) * wg::kIpBN + nl;
+            wp[e] = (n < G && k < I) ? w_ih[(size_t)n * I + k] : 0.0f;
+        }
     }
     for (long long e = t0; e < n_wht; e += stride) {
         const int k = (int)(e / NPR), n = (int)(e % NPR);
         wht[e] = (k < H && n < G) ? w_hh[(size_t)n * H + k] : 0.0f;
     }
-    for (long long e = t0; e < NPB; e += stride) {
+    for (long long e = t0; e < n_bias; e += stride) {
         float v = 0.0f;
         if (e < G) v = b_ih[e] + (e < 2 * H ? b_hh[e] : 0.0f);  // r,z: both biases; n: b_in only
         bias[e] = v;
@@ -159,7 +189,7 @@ __global__ void pack_params_kernel(const float* __restrict__ w_ih, const float* 
 // ---------------------------------------------------------------------------------------------
 template <int FP, int SG, bool EXACT, int LAYERS, bool TILED>
 int launch_gcn_t(const float* X, const float* adj, const float* W1, const float* b1, const float* W2,
-                 const float* b2, float* out, long long R, int S, int Fi, int Fh, int Fo, int ldo,
+                 const float* b2, float* out, float* out_lo, long long R, int S, int Fi, int Fh, int Fo, int ldo,
                  cudaStream_t st) {
     const int NSG = wg::ceil_div(S, SG);
     if (NSG > wg::kGcnThreads)
@@ -193,7 +223,8 @@ int launch_gcn_t(const float* X, const float* adj, const float* W1, const float*
     long long grid = (long long)wg::kNumSMs * per_sm;
     if (grid > nblocks) grid = nblocks;
     if (grid < 1) return WG_OK;
-    kern<<<(unsigned)grid, wg::kGcnThreads, smem, st>>>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, RB);
+    kern<<<(unsigned)grid, wg::kGcnThreads, smem, st>>>(X, adj, W1, b1, W2, b2, out, out_lo, R, S, Fi, Fh, Fo, ldo,
+                                                        RB);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -205,11 +236,11 @@ int pick_sg(int S) {
 
 template <int LAYERS, bool TILED>
 int launch_gcn(const float* X, const float* adj, const float* W1, const float* b1, const float* W2,
-               const float* b2, float* out, long long R, int S, int Fi, int Fh, int Fo, int ldo,
+               const float* b2, float* out, float* out_lo, long long R, int S, int Fi, int Fh, int Fo, int ldo,
                cudaStream_t st) {
     const int fmax = Fi > Fh ? (Fi > Fo ? Fi : Fo) : (Fh > Fo ? Fh : Fo);
 #define WG_GCN(FP, SG, EX) \
-    launch_gcn_t<FP, SG, EX, LAYERS, TILED>(X, adj, W1, b1, W2, b2, out, R, S, Fi, Fh, Fo, ldo, st)
+    launch_gcn_t<FP, SG, EX, LAYERS, TILED>(X, adj, W1, b1, W2, b2, out, out_lo, R, S, Fi, Fh, Fo, ldo, st)
     if (Fi == 13 && Fh == 13 && Fo == 13) return pick_sg(S) == 7 ? WG_GCN(13, 7, true) : WG_GCN(13, 4, true);
     if (fmax <= 16) return WG_GCN(16, 4, false);
 #undef WG_GCN
@@ -249,7 +280,24 @@ int launch_gcn_sparse(const Plan& p, void* ws, const Csr& g, const float* x, con
     return WG_OK;
 }
 
+int launch_inproj_tc(const Plan& p, void* ws, long long rows, cudaStream_t st) {
+    const long long m_tiles = (rows + wg::kTcBM - 1) / wg::kTcBM;
+    if (m_tiles < 1) return WG_OK;
+    const wg::TcShape& t = p.tcs;
+    WG_CUDA(cudaFuncSetAttribute(wg::inproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)t.smem_bytes));
+    const long long tiles = m_tiles * t.n_nt;
+    const unsigned grid = (unsigned)(tiles < wg::kNumSMs ? tiles : wg::kNumSMs);
+    wg::inproj_tc_kernel<<<grid, wg::kTcThreads, t.smem_bytes, st>>>(
+        ws_ptr<float>(ws, p.off_u), ws_ptr<float>(ws, p.off_u_lo), ws_ptr<float>(ws, p.off_wp),
+        ws_ptr<float>(ws, p.off_wp_lo), ws_ptr<float>(ws, p.off_bias), ws_ptr<float>(ws, p.off_gi), rows, p.IP, p.GP,
+        t.n_nt, t.N_each, t.stages);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
 int launch_inproj(const Plan& p, void* ws, long long rows, cudaStream_t st) {
+    if (p.tc) return launch_inproj_tc(p, ws, rows, st);
     const long long m_tiles = (rows + wg::kIpBM - 1) / wg::kIpBM;
     const int n_tiles = p.NPB / wg::kIpBN;
     const long long grid = m_tiles * n_tiles;
@@ -304,9 +352,11 @@ int launch_recur(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t
 
 int launch_pack(const Plan& p, void* ws, const float* w_ih, const float* w_hh, const float* b_ih,
                 const float* b_hh, cudaStream_t st) {
+    const int wrows = p.tc ? (p.tcs.NP > p.NPB ? p.tcs.NP : p.NPB) : p.NPB;
     pack_params_kernel<<<wg::kNumSMs * 2, 256, 0, st>>>(
-        w_ih, w_hh, b_ih, b_hh, ws_ptr<float>(ws, p.off_wp), ws_ptr<float>(ws, p.off_bias),
-        ws_ptr<float>(ws, p.off_wht), ws_ptr<float>(ws, p.off_bhn), p.I, p.H, p.IP, p.NPB, p.KP, p.NPR);
+        w_ih, w_hh, b_ih, b_hh, ws_ptr<float>(ws, p.off_wp), ws_ptr<float>(ws, p.off_wp_lo),
+        ws_ptr<float>(ws, p.off_bias), ws_ptr<float>(ws, p.off_wht), ws_ptr<float>(ws, p.off_bhn), p.I, p.H, p.IP,
+        p.NPB, p.KP, p.NPR, p.tc ? p.tcs.NP : 0, p.tcs.N_each, wrows > 512 ? wrows : 512);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -315,8 +365,9 @@ int launch_pack(const Plan& p, void* ws, const float* w_ih, const float* w_hh, c
 int run_chunk(const Plan& p, void* ws, const float* adj, const float* x, const float* w1, const float* b1,
               const float* w2, const float* b2, float* out, long long Bc, cudaStream_t st) {
     const long long rows = Bc * p.T;
-    int rc = launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_u), rows, p.S, p.Fi, p.Fh,
-                                 p.Fo, p.IP, st);
+    int rc = launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_u),
+                                 p.tc ? ws_ptr<float>(ws, p.off_u_lo) : nullptr, rows, p.S, p.Fi, p.Fh, p.Fo, p.IP,
+                                 st);
     if (rc) return rc;
     rc = launch_inproj(p, ws, rows, st);
     if (rc) return rc;
@@ -365,18 +416,18 @@ int wg_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); 
 const char* wg_last_error(void) { return g_err; }
 
 size_t wg_gcn_gru_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
-                                  int64_t chunk) {
+                                  int64_t chunk, int flags) {
     Plan p;
-    if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk)) return 0;
+    if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, false, flags)) return 0;
     return p.total;
 }
 
 int wg_stage_pack_f32(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int T,
-                      int S, int F_in, int F_hid, int F_out, int H, int64_t chunk, void* workspace,
+                      int S, int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags, void* workspace,
                       size_t workspace_bytes, int device, void* stream) {
     if (any_null({w_ih, w_hh, b_ih, b_hh})) return fail(WG_ERR_BAD_ARG, "null parameter pointer");
     Plan p;
-    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk);
+    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk, false, flags);
     if (rc) return rc;
     if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
     DeviceGuard g(device);
@@ -386,23 +437,24 @@ int wg_stage_pack_f32(const float* w_ih, const float* w_hh, const float* b_ih, c
 
 int wg_stage_gcn_f32(const float* adj, const float* x, const float* w1, const float* b1, const float* w2,
                      const float* b2, int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H,
-                     int64_t chunk, void* workspace, size_t workspace_bytes, int device, void* stream) {
+                     int64_t chunk, int flags, void* workspace, size_t workspace_bytes, int device, void* stream) {
     if (any_null({adj, x, w1, b1, w2, b2})) return fail(WG_ERR_BAD_ARG, "null pointer");
     Plan p;
-    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk);
+    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk, false, flags);
     if (rc) return rc;
     if (Bc < 0 || Bc > p.chunk) return fail(WG_ERR_BAD_ARG, "Bc=%lld outside [0, chunk=%lld]", (long long)Bc, p.chunk);
     if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
     DeviceGuard g(device);
     WG_CUDA(g.err);
-    return launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(workspace, p.off_u), (long long)Bc * T, S,
-                               F_in, F_hid, F_out, p.IP, static_cast<cudaStream_t>(stream));
+    return launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(workspace, p.off_u),
+                               p.tc ? ws_ptr<float>(workspace, p.off_u_lo) : nullptr, (long long)Bc * T, S, F_in,
+                               F_hid, F_out, p.IP, static_cast<cudaStream_t>(stream));
 }
 
 int wg_stage_inproj_f32(int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H, int64_t chunk,
-                        void* workspace, size_t workspace_bytes, int device, void* stream) {
+                        int flags, void* workspace, size_t workspace_bytes, int device, void* stream) {
     Plan p;
-    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk);
+    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk, false, flags);
     if (rc) return rc;
     if (Bc < 0 || Bc > p.chunk) return fail(WG_ERR_BAD_ARG, "Bc=%lld outside [0, chunk=%lld]", (long long)Bc, p.chunk);
     if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
@@ -412,10 +464,10 @@ int wg_stage_inproj_f32(int64_t Bc, int T, int S, int F_in, int F_hid, int F_out
 }
 
 int wg_stage_recur_f32(float* out, int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H,
-                       int64_t chunk, void* workspace, size_t workspace_bytes, int device, void* stream) {
+                       int64_t chunk, int flags, void* workspace, size_t workspace_bytes, int device, void* stream) {
     if (!out) return fail(WG_ERR_BAD_ARG, "null output pointer");
     Plan p;
-    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk);
+    int rc = make_plan(p, chunk, T, S, F_in, F_hid, F_out, H, chunk, false, flags);
     if (rc) return rc;
     if (Bc < 0 || Bc > p.chunk) return fail(WG_ERR_BAD_ARG, "Bc=%lld outside [0, chunk=%lld]", (long long)Bc, p.chunk);
     if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
@@ -427,10 +479,10 @@ int wg_stage_recur_f32(float* out, int64_t Bc, int T, int S, int F_in, int F_hid
 int wg_gcn_gru_forward_f32(const float* adj, const float* x, const float* w1, const float* b1,
                            const float* w2, const float* b2, const float* w_ih, const float* w_hh,
                            const float* b_ih, const float* b_hh, float* out, int64_t B, int T, int S,
-                           int F_in, int F_hid, int F_out, int H, int64_t chunk, void* workspace,
+                           int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags, void* workspace,
                            size_t workspace_bytes, int device, void* stream) {
     Plan p;
-    int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk);
+    int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, false, flags);
     if (rc) return rc;
     if (B == 0) return WG_OK;
     if (any_null({adj, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, out}))
@@ -488,9 +540,9 @@ int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, con
 // ---- host-buffer variant: H2D / compute / D2H of consecutive chunks overlapped ----------------
 // workspace = [ compute workspace | x staging 0 | x staging 1 | out staging 0 | out staging 1 ]
 size_t wg_gcn_gru_host_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
-                                       int64_t chunk) {
+                                       int64_t chunk, int flags) {
     Plan p;
-    if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk)) return 0;
+    if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, false, flags)) return 0;
     const size_t xs = align_up((size_t)p.chunk * T * S * F_in * 4);
     const size_t os = align_up((size_t)p.chunk * T * H * 4);
     return p.total + 2 * xs + 2 * os;
@@ -499,10 +551,10 @@ size_t wg_gcn_gru_host_workspace_bytes(int64_t B, int T, int S, int F_in, int F_
 int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const float* w1, const float* b1,
                                 const float* w2, const float* b2, const float* w_ih, const float* w_hh,
                                 const float* b_ih, const float* b_hh, float* out_host, int64_t B, int T,
-                                int S, int F_in, int F_hid, int F_out, int H, int64_t chunk,
+                                int S, int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags,
                                 void* workspace, size_t workspace_bytes, int device) {
     Plan p;
-    int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk);
+    int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, false, flags);
     if (rc) return rc;
     if (B == 0) return WG_OK;
     if (any_null({adj, x_host, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, out_host}))
@@ -602,7 +654,7 @@ int wg_gcn_layer_f32(const float* adj, const float* attr, const float* weight, c
     DeviceGuard g(device);
     WG_CUDA(g.err);
     // single layer: "hidden" plays the role of the output width
-    return launch_gcn<1, false>(attr, adj, weight, bias, nullptr, nullptr, out, R, S, F_in, F_out, F_out,
+    return launch_gcn<1, false>(attr, adj, weight, bias, nullptr, nullptr, out, nullptr, R, S, F_in, F_out, F_out,
                                 S * F_out, static_cast<cudaStream_t>(stream));
 }
 

@@ -134,7 +134,8 @@ template <int FP, int SG, bool EXACT, int LAYERS, bool TILED>
 __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
     gcn_kernel(const float* __restrict__ X, const float* __restrict__ adj, const float* __restrict__ W1,
                const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
-               float* __restrict__ out, long long R, int S, int Fi, int Fh, int Fo, int ldo, int RB) {
+               float* __restrict__ out, float* __restrict__ out_lo, long long R, int S, int Fi, int Fh, int Fo,
+               int ldo, int RB) {
     extern __shared__ __align__(16) float smem[];
     const int NSG = ceil_div(S, SG);
     const int tid = threadIdx.x;
@@ -213,7 +214,31 @@ __global__ void __launch_bounds__(kGcnThreads, WG_GCN_MINB)
             gcn_layer_inplace<FP, SG, EXACT>(buf, adjT, w2d, b2s, S, Fh, Fo, RS, NSG, row_local, q, active);
 
         // ---- store the final slab ----
-        if (TILED) {
+        if (TILED && out_lo != nullptr) {
+            // tensor-core layout (inproj_tc.cuh): out / out_lo [(r / 128)][c / 4][r % 128][4] hold the
+            // TF32-rounded value and the remainder; a lane owns one row and writes 16 bytes per
+            // column quad, so a warp store covers nrows * 16 contiguous bytes
+            for (int rl = tid & 31; rl < nrows; rl += 32) {
+                const long long r = r0 + rl;
+                const size_t base = ((size_t)(r / kUTileRows) * (ldo >> 2) * kUTileRows + (r % kUTileRows)) * 4;
+                const float* srcr = buf + rl * RS;
+                for (int cq = tid >> 5; cq < (ldo >> 2); cq += kGcnThreads / 32) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 4 * cq + j;
+                        const float v = c < out_cols ? srcr[c] : 0.0f;
+                        uint32_t t;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+                        hi[j] = __uint_as_float(t);
+                        lo[j] = v - hi[j];
+                    }
+                    const size_t o = base + (size_t)cq * kUTileRows * 4;
+                    *reinterpret_cast<float4*>(out + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(out_lo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        } else if (TILED) {
             // out[(r / 128)][c][r % 128]: a lane owns one row of the block (its tile offset is fixed),
             // each warp walks the columns; a store instruction writes nrows consecutive floats
             for (int rl = tid & 31; rl < nrows; rl += 32) {

@@ -47,6 +47,9 @@ class GCN_GRU(nn.Module):
         self.conv2 = GraphConvLayer(hidden_dim, output_dim)
         self.gru = nn.GRU(gru_input, gru_hidden_dim, batch_first=True)
         self.chunk = 0  # sequences per internal pass; 0 = library default
+        # "fp32": every contraction as FP32 FMA.  "tf32x3": the GRU input projection on the tcgen05
+        # tensor cores with error-compensated TF32 (same 1e-5 parity bar, see inproj_tc.cuh)
+        self.precision = "fp32"
         self._csr_cache = None  # (key, (rowptr, colidx, vals)) of the last large adjacency seen
 
     def forward(self, adj_matrix, attr_matrix):
@@ -67,7 +70,7 @@ class GCN_GRU(nn.Module):
                 self._csr_cache = (key, ops.dense_to_csr(adj_matrix))
             out = ops.gcn_gru_forward_csr(*self._csr_cache[1], attr_matrix, *params, self.chunk)
         else:
-            out = ops.gcn_gru_forward(adj_matrix, attr_matrix, *params, self.chunk)
+            out = ops.gcn_gru_forward(adj_matrix, attr_matrix, *params, self.chunk, self._flags())
         return out.squeeze(0)  # step6:26 — a no-op unless B == 1
 
     @torch.no_grad()
@@ -77,4 +80,14 @@ class GCN_GRU(nn.Module):
             self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
             self.gru.weight_ih_l0, self.gru.weight_hh_l0, self.gru.bias_ih_l0, self.gru.bias_hh_l0,
         )
-        return ops.gcn_gru_forward_host(adj_matrix, attr_host, [p.detach() for p in params], out_host, self.chunk)
+        return ops.gcn_gru_forward_host(adj_matrix, attr_host, [p.detach() for p in params], out_host, self.chunk,
+                                        flags=self._flags())
+
+    def _flags(self) -> int:
+        from . import _lib
+
+        if self.precision == "fp32":
+            return 0
+        if self.precision == "tf32x3":
+            return _lib.FLAG_TENSOR_CORES
+        raise ValueError(f"precision must be 'fp32' or 'tf32x3', got {self.precision!r}")

@@ -88,8 +88,10 @@ def gcn_gru_forward(
     b_ih: torch.Tensor,
     b_hh: torch.Tensor,
     chunk: int = 0,
+    flags: int = 0,
 ) -> torch.Tensor:
-    """``x [B,T,S,F_in] -> [B,T,H]`` (every GRU hidden state), fused on the GPU."""
+    """``x [B,T,S,F_in] -> [B,T,H]`` (every GRU hidden state), fused on the GPU.
+    ``flags``: 0 = FP32 FMA everywhere, ``_lib.FLAG_TENSOR_CORES`` = 3xTF32 tcgen05 input projection."""
     lib = _lib.load()
     x = _require_cuda_f32("attr_matrix", x)
     dev = x.device
@@ -105,23 +107,24 @@ def gcn_gru_forward(
     out = torch.empty((B, T, H), dtype=torch.float32, device=dev)
     if B == 0 or T == 0:
         return out
-    nbytes = lib.wg_gcn_gru_workspace_bytes(B, T, S, F_in, F_hid, F_out, H, chunk)
+    nbytes = lib.wg_gcn_gru_workspace_bytes(B, T, S, F_in, F_hid, F_out, H, chunk, flags)
     if nbytes == 0:
-        raise _lib.WindGNNError(_lib.WG_ERR_BAD_ARG, _lib.last_error())
+        raise _lib.WindGNNError(_lib.WG_ERR_UNSUPPORTED if "tensor-core" in _lib.last_error() else _lib.WG_ERR_BAD_ARG,
+                                _lib.last_error())
     ws = _workspace(dev, nbytes)
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(
         lib.wg_gcn_gru_forward_f32(
             adj.data_ptr(), x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
             w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), out.data_ptr(),
-            B, T, S, F_in, F_hid, F_out, H, chunk, ws.data_ptr(), ws.numel(), dev.index or 0, stream,
+            B, T, S, F_in, F_hid, F_out, H, chunk, flags, ws.data_ptr(), ws.numel(), dev.index or 0, stream,
         )
     )
     return out
 
 
 @gcn_gru_forward.register_fake
-def _(adj, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, chunk=0):
+def _(adj, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, chunk=0, flags=0):
     return x.new_empty((x.shape[0], x.shape[1], w_hh.shape[1]))
 
 
@@ -231,7 +234,7 @@ def _(adj, attr, weight, bias):
     return attr.new_empty((*attr.shape[:-1], weight.shape[1]))
 
 
-def gcn_gru_forward_host(adj, x_host, params, out_host=None, chunk: int = 0, device=None):
+def gcn_gru_forward_host(adj, x_host, params, out_host=None, chunk: int = 0, device=None, flags: int = 0):
     """End-to-end variant: ``x_host`` / ``out_host`` are HOST tensors (pin them for full
     copy/compute overlap); the batch is streamed through the GPU in chunks.  Blocks until
     ``out_host`` is complete.  ``params`` = the 8 tensors in state_dict order, on the GPU."""
@@ -248,7 +251,7 @@ def gcn_gru_forward_host(adj, x_host, params, out_host=None, chunk: int = 0, dev
         raise RuntimeError("out_host must be a contiguous float32 CPU tensor [B, T, H]")
     if B == 0:
         return out_host
-    nbytes = lib.wg_gcn_gru_host_workspace_bytes(B, T, S, F_in, F_hid, F_out, H, chunk)
+    nbytes = lib.wg_gcn_gru_host_workspace_bytes(B, T, S, F_in, F_hid, F_out, H, chunk, flags)
     if nbytes == 0:
         raise _lib.WindGNNError(_lib.WG_ERR_BAD_ARG, _lib.last_error())
     ws = _workspace(dev, nbytes, "host")
@@ -257,7 +260,7 @@ def gcn_gru_forward_host(adj, x_host, params, out_host=None, chunk: int = 0, dev
         lib.wg_gcn_gru_forward_host_f32(
             adj.data_ptr(), x_host.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
             w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), out_host.data_ptr(),
-            B, T, S, F_in, F_hid, F_out, H, chunk, ws.data_ptr(), ws.numel(), dev.index or 0,
+            B, T, S, F_in, F_hid, F_out, H, chunk, flags, ws.data_ptr(), ws.numel(), dev.index or 0,
         )
     )
     return out_host
