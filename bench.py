@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="sequences per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tensor-path", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3"],
                     help="fp32: every contraction as FP32 FMA; tf32x3: GRU input projection on tcgen05 (3xTF32)")
     ap.add_argument("--ref-seqs", type=int, default=512, help="sequences per step of the reference arm's sample")
@@ -295,6 +296,30 @@ def main():
     value = world * Bg * steps / (ms * 1e-3)
     n_chunks = (Bg + 148 * 32 - 1) // (148 * 32)
     launches_per_step = 1 + 3 * n_chunks  # pack + (gcn, inproj, recur) per internal chunk
+
+    # ---------------- the opt-in tensor-core path, same workload, same timing rules ----------------
+    tensor_path = None
+    if args.precision == "fp32" and not args.no_tensor_path:
+        model.precision = "tf32x3"
+        try:
+            with torch.no_grad():
+                for _ in range(warmup):
+                    yt = model(adj, x)
+                barrier()
+                t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0e.record()
+                for _ in range(steps):
+                    yt = model(adj, x)
+                t1e.record()
+                barrier()
+                ms_t = max_over_ranks(t0e.elapsed_time(t1e))
+            err = float((yt - y).abs().max() / y.abs().max())
+            tensor_path = {"precision": "tf32x3 (tcgen05 input projection, 3 TF32 products per term, fp32 accumulate)",
+                           "value": world * Bg * steps / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t / steps,
+                           "max_abs_diff_vs_fp32_path_normalised": err, "parity_bar": 1e-5}
+        finally:
+            model.precision = args.precision
+    barrier()
 
     # ---------------- per-kernel timing for the roofline (rank 0's GPU, same stream) -------------
     dims = (T, S, F, F, F, H)
@@ -402,7 +427,7 @@ def main():
                        "l2_policy": "inputs (1.22 GB per step) larger than L2",
                        "station_sequence_predictions_per_s": value * S},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "tensor_path": tensor_path,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
 #endif
     for (int t = 0; t < T; ++t) {
         WG_TRACE(0);
-#if WG_RC_ALTERNATE
+#if WG_RC_ALTERNATE == 2
+        group_barrier(5, NT);  // experiment: both groups start every step together
+#elif WG_RC_ALTERNATE
         // The two groups take turns on the FMA pipe: group 0 runs GEMM(t) while group 1 does the
         // merge / gates of step t-1, then they swap.  Barrier 3: "group 0 finished its GEMM",
         // barrier 4: "group 1 finished its GEMM" (arrive = signal, sync = wait; NT participants).
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
                     mma_frag(fa);
                 }
             }
-#if WG_RC_ALTERNATE
+#if WG_RC_ALTERNATE == 1
             if (cb + WG >= n_cb) {  // last column block of this warp: hand the FMA pipe over
                 if (grp == 0) group_arrive(3, NT);
                 else if (t + 1 < T) group_arrive(4, NT);
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
             merge_chunk(cB, IntC<4>{}, 2);
             merge_chunk(cC, IntC<2>{}, 4);
         }
-#if WG_RC_ALTERNATE
+#if WG_RC_ALTERNATE == 1
         if (!handed_over) {  // a warp without a column block still takes part in the hand-over
             if (grp == 0) group_arrive(3, NT);
             else if (t + 1 < T) group_arrive(4, NT);
