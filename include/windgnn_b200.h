@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WG_ABI_VERSION 2
+#define WG_ABI_VERSION 3
 
 /* `flags` of the GCN-GRU entry points */
 #define WG_FLAG_TENSOR_CORES 1 /* input projection on tcgen05 with error-compensated TF32 (3xTF32) */
@@ -183,6 +183,51 @@ int wg_make_windows_f32(const float* table, const int64_t* perm, float* x, float
                         int F, int L, int label_f, int horizons, int64_t N, int device, void* stream);
 int wg_denorm_last_step_f32(const float* out, float* pred, int64_t B, int T, int H, double vmin,
                             double vmax, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Training step — replaces the body of the reference's training loop (src/main.py:64-77):
+ *   outputs = model(adj_matrix, batch_x)            -> wg_gcn_gru_forward_train_f32
+ *   loss = nn.MSELoss()(outputs, batch_y)  (:49,:72) -> wg_mse_loss_grad_f32 (loss and dL/d outputs)
+ *   loss.backward()                        (:76)     -> wg_gcn_gru_backward_f32
+ *   optimizer.step()  (torch.optim.Adam, :52,:77)    -> wg_adam_step_f32
+ * FP32 throughout, dense adjacency, F_in / F_hid / F_out <= 16, H <= 128 (the shipped models).
+ *
+ * The forward is the inference path's three kernels; the recurrence additionally saves the gate
+ * values [r | z | n | W_hn h + b_hn] per (sequence, step).  `workspace` (sized by
+ * wg_gcn_gru_train_workspace_bytes for the same dims, 256-byte aligned) carries the saved state
+ * from the forward to the backward call and must not be touched in between.
+ *
+ * Backward: `out` is the forward's result, `d_out` [B, T, H] the gradient w.r.t. every hidden
+ * state.  `grads` receives (overwrites) ONE flat fp32 buffer of wg_gcn_gru_param_count floats in
+ * state_dict order  conv1.weight | conv1.bias | conv2.weight | conv2.bias | gru.weight_ih_l0 |
+ * gru.weight_hh_l0 | gru.bias_ih_l0 | gru.bias_hh_l0  — one bucket, so that a data-parallel job
+ * all-reduces it with a single collective.  No gradient is produced for x or adj (data).
+ * All reductions run in a fixed order: the gradients are bit-reproducible run to run.
+ * ---------------------------------------------------------------------------------- */
+size_t wg_gcn_gru_param_count(int S, int F_in, int F_hid, int F_out, int H);
+size_t wg_gcn_gru_train_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H);
+int wg_gcn_gru_forward_train_f32(const float* adj, const float* x, const float* w1, const float* b1,
+                                 const float* w2, const float* b2, const float* w_ih, const float* w_hh,
+                                 const float* b_ih, const float* b_hh, float* out, int64_t B, int T, int S,
+                                 int F_in, int F_hid, int F_out, int H, void* workspace, size_t workspace_bytes,
+                                 int device, void* stream);
+int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, const float* b1, const float* w2,
+                            const float* b2, const float* w_ih, const float* w_hh, const float* out,
+                            const float* d_out, float* grads, int64_t B, int T, int S, int F_in, int F_hid,
+                            int F_out, int H, void* workspace, size_t workspace_bytes, int device, void* stream);
+
+/* Mean-squared-error loss over n elements and its gradient: *loss = mean((out - y)^2) (device
+ * scalar), d_out = 2 (out - y) / n (may be NULL).  workspace: wg_mse_workspace_bytes() bytes. */
+size_t wg_mse_workspace_bytes(void);
+int wg_mse_loss_grad_f32(const float* out, const float* y, int64_t n, float* d_out, float* loss, void* workspace,
+                         size_t workspace_bytes, int device, void* stream);
+
+/* One torch.optim.Adam step (no weight decay / amsgrad) over flat buffers of n floats; `step` is
+ * the 1-based step count, `grad_scale` multiplies the gradient first (1 / world size after a
+ * sum all-reduce). */
+int wg_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                     double beta1, double beta2, double eps, int64_t step, double grad_scale, int device,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Measurement helper: sustained FP32 FFMA throughput of this device in TFLOP/s (2 flops per

@@ -25,7 +25,7 @@ def test_library_builds_and_loads():
     path = build.build()
     assert os.path.exists(path)
     lib = _lib.load()
-    assert lib.wg_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.wg_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_every_declared_symbol_is_exported():
@@ -81,3 +81,26 @@ def test_argument_validation_happens_before_cuda():
     assert rc == _lib.WG_ERR_WORKSPACE and "too small" in _lib.last_error()
     rc = lib.wg_gcn_gru_forward_f32(*([fake] * 11), 2, *dims, 0, 0, ctypes.c_void_p(addr + 4), 1 << 30, 0, None)
     assert rc == _lib.WG_ERR_WORKSPACE and "aligned" in _lib.last_error()
+
+
+def test_training_planning_and_validation():
+    lib = _lib.load()
+    dims34 = (168, 34, 13, 13, 13, 102)
+    n34 = 13 * 13 + 13 + 13 * 13 + 13 + 306 * 442 + 306 * 102 + 306 + 306
+    assert lib.wg_gcn_gru_param_count(34, 13, 13, 13, 102) == n34 == 167440
+    assert lib.wg_gcn_gru_param_count(7, 13, 13, 13, 21) == 7546
+    fwd = lib.wg_gcn_gru_workspace_bytes(512, *dims34, 512, 0)
+    trn = lib.wg_gcn_gru_train_workspace_bytes(512, *dims34)
+    # saved gates + DG (4H each) + dU (I) per row on top of the forward's scratch
+    assert trn - fwd >= 512 * 168 * (2 * 408 + 442) * 4
+    assert lib.wg_gcn_gru_train_workspace_bytes(512, 168, 34, 13, 32, 13, 102) == 0
+    assert "feature widths" in _lib.last_error()
+    assert lib.wg_mse_workspace_bytes() >= 8
+    fake = ctypes.c_void_p(8)
+    rc = lib.wg_gcn_gru_forward_train_f32(*([fake] * 11), 2, *dims34, None, 0, 0, None)
+    assert rc == _lib.WG_ERR_WORKSPACE
+    rc = lib.wg_gcn_gru_backward_f32(*([None] * 11), 2, *dims34, None, 0, 0, None)
+    assert rc == _lib.WG_ERR_BAD_ARG and "null" in _lib.last_error()
+    assert lib.wg_mse_loss_grad_f32(None, None, 0, None, None, None, 0, 0, None) == _lib.WG_ERR_BAD_ARG
+    assert lib.wg_adam_step_f32(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, 0, None) == _lib.WG_ERR_BAD_ARG
+    assert lib.wg_adam_step_f32(None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, 0, None) == _lib.WG_OK

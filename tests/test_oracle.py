@@ -132,3 +132,45 @@ def test_knn_graph_properties():
     m = knn_pattern(np.array([[0.0, 1.0, 1.0], [1.0, 0.0, 4.0], [1.0, 4.0, 0.0]]), 1)
     # ties broken by lower index: node 0 picks 1; 1 picks 0; 2 picks 0
     assert m.tolist() == [[True, True, True], [True, True, False], [True, False, True]]
+
+
+# ---------------------------------------------------------------------------------------------
+# training-step oracle (oracle/train_oracle.py) against the reference's own autograd + Adam
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S", [7, 34])
+def test_train_oracle_matches_reference_autograd(S):
+    from oracle.gcn_gru_oracle import PARAM_KEYS
+    from oracle.train_oracle import gcn_gru_loss_and_grads
+
+    g = golden(f"train_{S}.npz")
+    sd = load_checkpoint(S)
+    adj = golden(f"adj_ref_{S}.npy").astype(np.float32)
+    loss, _, G = gcn_gru_loss_and_grads(adj, g["x"], g["y"], sd, dtype=np.float64)
+    assert abs(loss - float(g["loss"])) <= 1e-12
+    for k in PARAM_KEYS:
+        ref = g["grad__" + k.replace(".", "__")]
+        assert G[k].shape == ref.shape
+        assert normalised_max_error(G[k], ref) <= 2e-7, k          # fixtures are stored as fp32
+        # and the reference's own fp32 run is within the bar the GPU path is held to
+        assert normalised_max_error(g["grad32__" + k.replace(".", "__")], ref) <= 1e-5, k
+
+
+def test_train_oracle_adam_trajectory_matches_reference():
+    from oracle.gcn_gru_oracle import PARAM_KEYS
+    from oracle.train_oracle import adam_step, gcn_gru_loss_and_grads
+
+    S = 7
+    g = golden(f"train_{S}.npz")
+    adj = golden(f"adj_ref_{S}.npy").astype(np.float32)
+    P = {k: v.numpy().astype(np.float64) for k, v in load_checkpoint(S).items()}
+    M = {k: np.zeros_like(v) for k, v in P.items()}
+    V = {k: np.zeros_like(v) for k, v in P.items()}
+    losses = []
+    for step in (1, 2, 3):
+        loss, _, G = gcn_gru_loss_and_grads(adj, g["x"], g["y"], P, dtype=np.float64)
+        losses.append(loss)
+        for k in PARAM_KEYS:
+            P[k], M[k], V[k] = adam_step(P[k], G[k], M[k], V[k], step)
+    np.testing.assert_allclose(losses, g["losses3"], rtol=1e-9)
+    for k in PARAM_KEYS:
+        np.testing.assert_allclose(P[k], g["param3__" + k.replace(".", "__")], atol=1e-7)

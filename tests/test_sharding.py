@@ -85,3 +85,59 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ---- data-parallel training: one flat gradient bucket, one all-reduce, mean folded into the optimiser ----
+def _train_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+
+        from oracle.train_oracle import adam_step
+        from windgnn_b200.train import allreduce_mean_, split_flat
+
+        shapes = [(3, 2), (2,), (4, 3), (4,)]
+        n = sum(int(np.prod(s)) for s in shapes)
+        # each rank's "local gradient": deterministic, different per rank
+        local = torch.arange(n, dtype=torch.float32) * (rank + 1) - 3.0
+        bucket = local.clone()
+        scale = allreduce_mean_(bucket)
+        views = split_flat(bucket, shapes)
+        # what the optimiser then does (the CUDA Adam kernel applies `scale` itself): oracle Adam on CPU
+        p0 = np.linspace(-1, 1, n)
+        p1, _, _ = adam_step(p0, bucket.numpy().astype(np.float64) * scale, np.zeros(n), np.zeros(n), 1)
+        q.put((rank, scale, bucket.tolist(), [tuple(v.shape) for v in views], p1.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_bucket_allreduce():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 6 + 2 + 12 + 4
+    expect_sum = [(i * 1 - 3.0) + (i * 2 - 3.0) for i in range(n)]
+    (r0, s0, b0, sh0, p0), (r1, s1, b1, sh1, p1) = results
+    assert s0 == s1 == 0.5
+    assert b0 == b1 == expect_sum                      # both ranks hold the summed bucket
+    assert sh0 == [(3, 2), (2,), (4, 3), (4,)]
+    assert p0 == p1                                    # replicas stay bit-identical after the step
+
+
+def test_allreduce_mean_is_identity_without_a_process_group():
+    from windgnn_b200.train import allreduce_mean_, split_flat
+
+    t = torch.arange(5.0)
+    assert allreduce_mean_(t) == 1.0 and t.tolist() == [0, 1, 2, 3, 4]
+    with pytest.raises(RuntimeError):
+        split_flat(t, [(2,), (2,)])

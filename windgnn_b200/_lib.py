@@ -18,7 +18,7 @@ WG_ERR_BAD_ARG = -1
 WG_ERR_UNSUPPORTED = -2
 WG_ERR_WORKSPACE = -3
 WG_ERR_CUDA = -4
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_TENSOR_CORES = 1
 
 
@@ -54,6 +54,14 @@ _SIGNATURES = {
     "wg_make_windows_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, _P]),
     "wg_denorm_last_step_f32": (c_int, [_P, _P, c_int64, c_int, c_int, c_double, c_double, c_int, _P]),
     "wg_measure_ffma_tflops": (c_double, [c_int, c_int]),
+    "wg_gcn_gru_param_count": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "wg_gcn_gru_train_workspace_bytes": (c_size_t, [c_int64, *_DIMS]),
+    "wg_gcn_gru_forward_train_f32": (c_int, [_P] * 11 + [c_int64, *_DIMS, _P, c_size_t, c_int, _P]),
+    "wg_gcn_gru_backward_f32": (c_int, [_P] * 11 + [c_int64, *_DIMS, _P, c_size_t, c_int, _P]),
+    "wg_mse_workspace_bytes": (c_size_t, []),
+    "wg_mse_loss_grad_f32": (c_int, [_P, _P, c_int64, _P, _P, _P, c_size_t, c_int, _P]),
+    "wg_adam_step_f32": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64,
+                                 c_double, c_int, _P]),
 }
 
 _lib = None

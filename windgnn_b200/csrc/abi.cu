@@ -3,15 +3,20 @@
 
 #include "../../include/windgnn_b200.h"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 
 #include "gcn.cuh"
+#include "gcn_bwd.cuh"
 #include "gcn_sparse.cuh"
+#include "gru_bwd.cuh"
 #include "inproj.cuh"
 #include "inproj_tc.cuh"
 #include "recur.cuh"
+#include "sgemm.cuh"
+#include "train_misc.cuh"
 #include "wg_common.cuh"
 
 namespace {
@@ -312,8 +317,9 @@ int launch_inproj(const Plan& p, void* ws, long long rows, cudaStream_t st) {
     return WG_OK;
 }
 
-template <int NW, bool WS>
-int launch_recur_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
+template <int NW, bool WS, bool SAVE = false>
+int launch_recur_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave = nullptr,
+                   int ldsave = 0) {
     // stage h in shared memory for bulk stores when it fits, else store every step directly
     int TS = wg::recur_stage_steps(p.H);
     size_t smem = wg::recur_smem_floats(p.KP, p.NPR, p.GP, WS, p.H, TS) * 4;
@@ -321,13 +327,13 @@ int launch_recur_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream
         TS = 0;
         smem = wg::recur_smem_floats(p.KP, p.NPR, p.GP, WS) * 4;
     }
-    auto kern = wg::gru_recur_kernel<NW, WS>;
+    auto kern = wg::gru_recur_kernel<NW, WS, SAVE>;
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (Bc + wg::kRcBT - 1) / wg::kRcBT;
     if (grid < 1) return WG_OK;
     kern<<<(unsigned)grid, NW * 32, smem, st>>>(ws_ptr<float>(ws, p.off_gi), ws_ptr<float>(ws, p.off_wht),
                                                ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, p.GP,
-                                               p.KP, p.NPR, TS);
+                                               p.KP, p.NPR, TS, gsave, ldsave);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -340,6 +346,18 @@ int launch_recur_ws(const Plan& p, void* ws, float* out, long long Bc, cudaStrea
     if (blocks <= 2) return launch_recur_t<4, WS>(p, ws, out, Bc, st);
     if (blocks <= 4) return launch_recur_t<8, WS>(p, ws, out, Bc, st);
     return launch_recur_t<16, WS>(p, ws, out, Bc, st);
+}
+
+// training forward: the same recurrence, additionally saving [r | z | n | hn] per (sequence, step)
+int launch_recur_save(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
+    const size_t smem_ws = wg::recur_smem_floats(p.KP, p.NPR, p.GP, true) * 4;
+    if (smem_ws > (size_t)wg::kMaxSmemOptin)
+        return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d does not fit the shared-memory recurrence", p.H);
+    const int blocks = p.NPR / wg::kRcCB;
+    if (blocks <= 1) return launch_recur_t<2, true, true>(p, ws, out, Bc, st, gsave, ldsave);
+    if (blocks <= 2) return launch_recur_t<4, true, true>(p, ws, out, Bc, st, gsave, ldsave);
+    if (blocks <= 4) return launch_recur_t<8, true, true>(p, ws, out, Bc, st, gsave, ldsave);
+    return launch_recur_t<16, true, true>(p, ws, out, Bc, st, gsave, ldsave);
 }
 
 int launch_recur(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
@@ -388,6 +406,119 @@ bool any_null(std::initializer_list<const void*> ps) {
     for (const void* q : ps)
         if (!q) return true;
     return false;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// training step: forward that saves the gate values, backward (BPTT + GEMMs + GCN backward)
+// ---------------------------------------------------------------------------------------------
+struct TrainPlan {
+    Plan f;            // the forward's plan (chunk == B, FP32 path, dense graph)
+    int LD4;           // row stride of the gate / DG buffers: 4H rounded up to 4
+    int HP, GR;        // gru_bwd: H rounded up to 4, 3H rounded up to 8
+    long long rows;    // B * T
+    int grid_gb;       // CTAs of the backward recurrence
+    int grid_gcn, rb_gcn, sg_gcn, fp_gcn;
+    size_t smem_gcn;
+    int splits_hh_a, splits_hh_b, splits_ih;
+    size_t off_gates, off_dg, off_du, off_biasp, off_gcnp, off_splitk, total;
+};
+
+int pick_splits(long long M, long long N, long long K) {
+    const long long tiles = ((M + wg::kSgBM - 1) / wg::kSgBM) * ((N + wg::kSgBN - 1) / wg::kSgBN);
+    long long s = (2LL * wg::kNumSMs + tiles - 1) / tiles;
+    const long long kmax = (K + 63) / 64;  // at least 64 k's per split
+    if (s > kmax) s = kmax;
+    return s < 1 ? 1 : (int)s;
+}
+
+size_t param_count(int S, int Fi, int Fh, int Fo, int H) {
+    const size_t I = (size_t)S * Fo, G = 3 * (size_t)H;
+    return (size_t)Fi * Fh + Fh + (size_t)Fh * Fo + Fo + G * I + G * H + G + G;
+}
+
+int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, int Fo, int H) {
+    int rc = make_plan(tp.f, B, T, S, Fi, Fh, Fo, H, B > 0 ? B : 1, false, 0);
+    if (rc) return rc;
+    const Plan& p = tp.f;
+    if (Fi > 16 || Fh > 16 || Fo > 16)
+        return fail(WG_ERR_UNSUPPORTED, "training: GCN feature widths must be <= 16 (got %d / %d / %d)", Fi, Fh, Fo);
+    tp.LD4 = wg::round_up(4 * H, 4);
+    tp.HP = wg::round_up(H, 4);
+    tp.GR = wg::round_up(3 * H, 8);
+    if (tp.HP > 128 || wg::gru_bwd_smem_floats(tp.HP, tp.GR) * 4 > (size_t)wg::kMaxSmemOptin)
+        return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d too large for the shared-memory BPTT kernel", H);
+    tp.rows = (B > 0 ? B : 1) * (long long)T;
+    tp.grid_gb = (int)(((B > 0 ? B : 1) + wg::kGbBT - 1) / wg::kGbBT);
+    // GCN backward geometry (same station grouping as the forward)
+    tp.sg_gcn = pick_sg(S);
+    tp.fp_gcn = (Fi == 13 && Fh == 13 && Fo == 13) ? 13 : 16;
+    if (tp.fp_gcn == 16) tp.sg_gcn = 4;
+    const int NSG = wg::ceil_div(S, tp.sg_gcn);
+    if (NSG > wg::kGcnThreads) return fail(WG_ERR_UNSUPPORTED, "training: S=%d too large for the dense GCN kernels", S);
+    int RB = wg::kGcnThreads / NSG;
+    const int cols = S * Fi, dcols = S * Fo;
+    const int need = ((cols % 4 == 0) && (dcols % 4 == 0)) ? 1 : ((cols % 2 == 0) && (dcols % 2 == 0)) ? 2 : 4;
+    if (RB > need) RB -= RB % need;
+    auto smem_of = [&](int rb) {
+        return (tp.sg_gcn == 7 ? wg::gcn_bwd_smem_floats<7>(S, Fo, rb) : wg::gcn_bwd_smem_floats<4>(S, Fo, rb)) * 4;
+    };
+    while (smem_of(RB) > (size_t)wg::kMaxSmemOptin && RB > 1) RB = (RB > need) ? RB - need : RB - 1;
+    if (smem_of(RB) > (size_t)wg::kMaxSmemOptin)
+        return fail(WG_ERR_UNSUPPORTED, "training: S=%d does not fit the shared-memory GCN backward", S);
+    tp.rb_gcn = RB;
+    tp.smem_gcn = smem_of(RB);
+    const long long nblk = (tp.rows + RB - 1) / RB;
+    tp.grid_gcn = (int)(nblk < wg::kNumSMs ? nblk : wg::kNumSMs);
+    tp.splits_hh_a = pick_splits(2 * H, H, tp.rows);
+    tp.splits_hh_b = pick_splits(H, H, tp.rows);
+    tp.splits_ih = pick_splits(p.I, p.G, tp.rows);
+    size_t o = p.total;
+    tp.off_gates = o; o = align_up(o + (size_t)tp.rows * tp.LD4 * 4);
+    tp.off_dg = o;    o = align_up(o + (size_t)tp.rows * tp.LD4 * 4);
+    tp.off_du = o;    o = align_up(o + (size_t)tp.rows * p.I * 4);
+    tp.off_biasp = o; o = align_up(o + (size_t)tp.grid_gb * 2 * tp.LD4 * 4);
+    tp.off_gcnp = o;  o = align_up(o + (size_t)tp.grid_gcn * (wg::kGcnThreads / 16) * (2 * 256 + 32) * 4);
+    size_t sk = (size_t)tp.splits_hh_a * 2 * H * H;
+    if ((size_t)tp.splits_hh_b * H * H > sk) sk = (size_t)tp.splits_hh_b * H * H;
+    if ((size_t)tp.splits_ih * p.I * p.G > sk) sk = (size_t)tp.splits_ih * p.I * p.G;
+    tp.off_splitk = o; o = align_up(o + sk * 4);
+    tp.total = o;
+    return WG_OK;
+}
+
+bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+// C[M][N] (strided out[m * s_m + n * s_n]) = A . B with K split over `splits` CTAs per tile.
+int splitk_gemm(const wg::SgOperand& A, const wg::SgOperand& Bo, long long M, int N, long long K, int splits,
+                float* part, float* out, long long s_m, long long s_n, cudaStream_t st) {
+    if (M < 1 || N < 1) return WG_OK;
+    long long kper = (K + splits - 1) / splits;
+    kper = (kper + wg::kSgBK - 1) / wg::kSgBK * wg::kSgBK;
+    const dim3 grid((unsigned)((N + wg::kSgBN - 1) / wg::kSgBN), (unsigned)((M + wg::kSgBM - 1) / wg::kSgBM),
+                    (unsigned)splits);
+    WG_CUDA(cudaFuncSetAttribute(wg::sgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSgSmemBytes));
+    // splits == 1 still goes through `part` (dense [M][N]) so that the strided write is in one place
+    wg::sgemm_kernel<<<grid, wg::kSgThreads, wg::kSgSmemBytes, st>>>(A, Bo, part, N, M, N, K, kper);
+    WG_CUDA(cudaGetLastError());
+    const long long total = M * N;
+    const unsigned rgrid = (unsigned)((total + 255) / 256 < 4 * wg::kNumSMs ? (total + 255) / 256 : 4 * wg::kNumSMs);
+    wg::sg_reduce_kernel<<<rgrid, 256, 0, st>>>(part, splits, M, N, out, s_m, s_n);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+template <int FP, int SG>
+int launch_gcn_bwd_t(const TrainPlan& tp, void* ws, const float* x, const float* adj, const float* w1, const float* b1,
+                     const float* w2, const float* b2, cudaStream_t st) {
+    const Plan& p = tp.f;
+    auto kern = wg::gcn_bwd_kernel<FP, SG>;
+    WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_gcn));
+    kern<<<tp.grid_gcn, wg::kGcnThreads, tp.smem_gcn, st>>>(x, ws_ptr<float>(ws, tp.off_du), adj, w1, b1, w2, b2,
+                                                           ws_ptr<float>(ws, tp.off_gcnp), tp.rows, p.S, p.Fi, p.Fh,
+                                                           p.Fo, tp.rb_gcn);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
 }
 
 // FFMA peak microbenchmark: 8 independent chains per thread, register resident.
@@ -656,6 +787,172 @@ int wg_gcn_layer_f32(const float* adj, const float* attr, const float* weight, c
     // single layer: "hidden" plays the role of the output width
     return launch_gcn<1, false>(attr, adj, weight, bias, nullptr, nullptr, out, nullptr, R, S, F_in, F_out, F_out,
                                 S * F_out, static_cast<cudaStream_t>(stream));
+}
+
+
+// ---- training step --------------------------------------------------------------------------
+size_t wg_gcn_gru_param_count(int S, int F_in, int F_hid, int F_out, int H) {
+    if (S <= 0 || F_in <= 0 || F_hid <= 0 || F_out <= 0 || H <= 0) return 0;
+    return param_count(S, F_in, F_hid, F_out, H);
+}
+
+size_t wg_gcn_gru_train_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H) {
+    TrainPlan tp;
+    if (make_train_plan(tp, B, T, S, F_in, F_hid, F_out, H)) return 0;
+    return tp.total;
+}
+
+int wg_gcn_gru_forward_train_f32(const float* adj, const float* x, const float* w1, const float* b1,
+                                 const float* w2, const float* b2, const float* w_ih, const float* w_hh,
+                                 const float* b_ih, const float* b_hh, float* out, int64_t B, int T, int S,
+                                 int F_in, int F_hid, int F_out, int H, void* workspace, size_t workspace_bytes,
+                                 int device, void* stream) {
+    TrainPlan tp;
+    int rc = make_train_plan(tp, B, T, S, F_in, F_hid, F_out, H);
+    if (rc) return rc;
+    if (B == 0) return WG_OK;
+    if (any_null({adj, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, out}))
+        return fail(WG_ERR_BAD_ARG, "null pointer argument");
+    if (!workspace || reinterpret_cast<uintptr_t>(workspace) % kAlign)
+        return fail(WG_ERR_WORKSPACE, "workspace NULL or not %zu-byte aligned", kAlign);
+    if (workspace_bytes < tp.total)
+        return fail(WG_ERR_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, tp.total);
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Plan& p = tp.f;
+    if ((rc = launch_pack(p, workspace, w_ih, w_hh, b_ih, b_hh, st))) return rc;
+    if ((rc = launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(workspace, p.off_u), nullptr, tp.rows, S, F_in,
+                                  F_hid, F_out, p.IP, st)))
+        return rc;
+    if ((rc = launch_inproj(p, workspace, tp.rows, st))) return rc;
+    return launch_recur_save(p, workspace, out, B, st, ws_ptr<float>(workspace, tp.off_gates), tp.LD4);
+}
+
+int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, const float* b1, const float* w2,
+                            const float* b2, const float* w_ih, const float* w_hh, const float* out,
+                            const float* d_out, float* grads, int64_t B, int T, int S, int F_in, int F_hid,
+                            int F_out, int H, void* workspace, size_t workspace_bytes, int device, void* stream) {
+    TrainPlan tp;
+    int rc = make_train_plan(tp, B, T, S, F_in, F_hid, F_out, H);
+    if (rc) return rc;
+    if (any_null({adj, x, w1, b1, w2, b2, w_ih, w_hh, out, d_out, grads}))
+        return fail(WG_ERR_BAD_ARG, "null pointer argument");
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Plan& p = tp.f;
+    const size_t n_params = param_count(S, F_in, F_hid, F_out, H);
+    if (B == 0) {
+        WG_CUDA(cudaMemsetAsync(grads, 0, n_params * 4, st));
+        return WG_OK;
+    }
+    if (!workspace || reinterpret_cast<uintptr_t>(workspace) % kAlign)
+        return fail(WG_ERR_WORKSPACE, "workspace NULL or not %zu-byte aligned", kAlign);
+    if (workspace_bytes < tp.total)
+        return fail(WG_ERR_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, tp.total);
+    // flat gradient layout = state_dict order
+    float* d_w1 = grads;
+    float* d_b1 = d_w1 + (size_t)F_in * F_hid;
+    float* d_w2 = d_b1 + F_hid;
+    float* d_b2 = d_w2 + (size_t)F_hid * F_out;
+    float* d_wih = d_b2 + F_out;
+    float* d_whh = d_wih + (size_t)p.G * p.I;
+    float* d_bih = d_whh + (size_t)p.G * H;
+    float* d_bhh = d_bih + p.G;
+
+    float* gates = ws_ptr<float>(workspace, tp.off_gates);
+    float* DG = ws_ptr<float>(workspace, tp.off_dg);
+    float* dU = ws_ptr<float>(workspace, tp.off_du);
+    float* biasp = ws_ptr<float>(workspace, tp.off_biasp);
+    float* skp = ws_ptr<float>(workspace, tp.off_splitk);
+    const long long rows = tp.rows;
+
+    // 1. BPTT through the recurrence: DG = [da_r | da_z | da_n | da_n r], bias partials
+    {
+        const size_t smem = wg::gru_bwd_smem_floats(tp.HP, tp.GR) * 4;
+        WG_CUDA(cudaFuncSetAttribute(wg::gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wg::gru_bwd_kernel<<<tp.grid_gb, wg::kGbThreads, smem, st>>>(gates, out, d_out, w_hh, DG, biasp, B, T, H, tp.LD4,
+                                                                    tp.HP, tp.GR);
+        WG_CUDA(cudaGetLastError());
+        wg::gru_bias_grad_kernel<<<(4 * H + 127) / 128, 128, 0, st>>>(biasp, tp.grid_gb * 2, H, tp.LD4, d_bih, d_bhh);
+        WG_CUDA(cudaGetLastError());
+    }
+    const int dg_vec = (tp.LD4 % 4 == 0) && aligned16(DG);
+    // 2. dW_hh = dGH^T . H_prev   (H_prev[b, t] = out[b, t-1], 0 at t = 0)
+    {
+        const wg::SgOperand hprev{out, H, 0, 0, (H % 4 == 0) && aligned16(out), T};
+        const wg::SgOperand a_rz{DG, tp.LD4, 0, 0, dg_vec, 0};
+        if ((rc = splitk_gemm(a_rz, hprev, 2 * H, H, rows, tp.splits_hh_a, skp, d_whh, H, 1, st))) return rc;
+        const wg::SgOperand a_n{DG + 3 * (size_t)H, tp.LD4, 0, 0, dg_vec && ((3 * H) % 4 == 0), 0};
+        if ((rc = splitk_gemm(a_n, hprev, H, H, rows, tp.splits_hh_b, skp, d_whh + 2 * (size_t)H * H, H, 1, st)))
+            return rc;
+    }
+    // 3. dW_ih^T [I x 3H] = U^T . dGI   (U in the forward's K-major tiles), written transposed
+    {
+        const wg::SgOperand a_u{ws_ptr<float>(workspace, p.off_u), p.IP, 1, 1, 1, 0};
+        const wg::SgOperand b_dg{DG, tp.LD4, 0, 0, dg_vec, 0};
+        if ((rc = splitk_gemm(a_u, b_dg, p.I, p.G, rows, tp.splits_ih, skp, d_wih, 1, p.I, st))) return rc;
+    }
+    // 4. dU [BT x I] = dGI . W_ih
+    {
+        const wg::SgOperand a_dg{DG, tp.LD4, 1, 0, dg_vec, 0};
+        const wg::SgOperand b_w{w_ih, p.I, 0, 0, (p.I % 4 == 0) && aligned16(w_ih), 0};
+        const dim3 grid((unsigned)((p.I + wg::kSgBN - 1) / wg::kSgBN), (unsigned)((rows + wg::kSgBM - 1) / wg::kSgBM), 1);
+        if (grid.y > 65535u) return fail(WG_ERR_UNSUPPORTED, "training: B*T = %lld rows exceed the GEMM grid", rows);
+        WG_CUDA(cudaFuncSetAttribute(wg::sgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSgSmemBytes));
+        wg::sgemm_kernel<<<grid, wg::kSgThreads, wg::kSgSmemBytes, st>>>(a_dg, b_w, dU, p.I, rows, p.I, p.G,
+                                                                        (long long)wg::round_up(p.G, wg::kSgBK));
+        WG_CUDA(cudaGetLastError());
+    }
+    // 5. GCN backward: dW1, db1, dW2, db2
+    if (tp.fp_gcn == 13 && tp.sg_gcn == 7) rc = launch_gcn_bwd_t<13, 7>(tp, workspace, x, adj, w1, b1, w2, b2, st);
+    else if (tp.fp_gcn == 13) rc = launch_gcn_bwd_t<13, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
+    else rc = launch_gcn_bwd_t<16, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
+    if (rc) return rc;
+    wg::gcn_bwd_finish_kernel<<<(2 * 256 + 32 + 127) / 128, 128, 0, st>>>(
+        ws_ptr<float>(workspace, tp.off_gcnp), tp.grid_gcn * (wg::kGcnThreads / 16), F_in, F_hid, F_out, d_w1, d_b1,
+        d_w2, d_b2);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+size_t wg_mse_workspace_bytes(void) { return (size_t)2 * wg::kNumSMs * sizeof(double); }
+
+int wg_mse_loss_grad_f32(const float* out, const float* y, int64_t n, float* d_out, float* loss, void* workspace,
+                         size_t workspace_bytes, int device, void* stream) {
+    if (n <= 0) return fail(WG_ERR_BAD_ARG, "mse: n must be positive");
+    if (any_null({out, y, loss})) return fail(WG_ERR_BAD_ARG, "null pointer argument");
+    if (!workspace || workspace_bytes < wg_mse_workspace_bytes() || reinterpret_cast<uintptr_t>(workspace) % 8)
+        return fail(WG_ERR_WORKSPACE, "mse: workspace of %zu bytes (8-byte aligned) needed", wg_mse_workspace_bytes());
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = 2 * wg::kNumSMs;
+    wg::mse_grad_kernel<<<grid, wg::kMseThreads, 0, st>>>(out, y, d_out, static_cast<double*>(workspace), n,
+                                                         (float)(2.0 / (double)n));
+    WG_CUDA(cudaGetLastError());
+    wg::mse_finish_kernel<<<1, 32, 0, st>>>(static_cast<double*>(workspace), grid, n, loss);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
+int wg_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                     double beta1, double beta2, double eps, int64_t step, double grad_scale, int device,
+                     void* stream) {
+    if (n < 0 || step < 1) return fail(WG_ERR_BAD_ARG, "adam: n >= 0 and step >= 1 required");
+    if (n == 0) return WG_OK;
+    if (any_null({param, grad, exp_avg, exp_avg_sq})) return fail(WG_ERR_BAD_ARG, "null pointer argument");
+    DeviceGuard g(device);
+    WG_CUDA(g.err);
+    const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+    const long long blocks = (n + 255) / 256;
+    const unsigned grid = (unsigned)(blocks < 8LL * wg::kNumSMs ? blocks : 8LL * wg::kNumSMs);
+    wg::adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        param, grad, exp_avg, exp_avg_sq, n, (float)grad_scale, (float)beta1, (float)beta2, (float)(lr / bc1),
+        (float)sqrt(bc2), (float)eps);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
 }
 
 #ifdef WG_RC_TRACE

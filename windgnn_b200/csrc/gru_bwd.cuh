@@ -1,0 +1,228 @@
+// Backward of the GRU recurrence (BPTT) — all T steps, last to first, inside ONE launch.
+//
+// Reference: `loss.backward()` (src/main.py:76) through `self.gru(hidden2)`
+// (src/step6_gcn_gru_combined_model.py:23).  With the forward's saved gate values
+// (r, z, n, hn = W_hn h + b_hn) and h_prev = out[t-1] (0 at t = 0):
+//     g     = dL/dout[t] + dL/dh_t carried from step t+1
+//     dn    = g (1 - z)            dz = g (h_prev - n)
+//     da_n  = dn (1 - n^2)         da_z = dz z (1 - z)        da_r = da_n hn r (1 - r)
+//     dgi   = [da_r, da_z, da_n]   dgh  = [da_r, da_z, da_n r]
+//     dL/dh_{t-1} = g z + dgh . W_hh
+// The kernel writes DG[b, t, :] = [da_r | da_z | da_n | da_n r] (4H columns) for the three weight
+// / input GEMMs that follow (sgemm.cuh), and per-CTA column sums of DG for the bias gradients.
+//
+// A CTA owns 16 sequences; W_hh ([3H][H] as PyTorch stores it — already "contraction-major" for
+// dgh . W_hh) stays in shared memory for the whole kernel.  Per step: the gate phase (thread = hidden
+// unit x half of the sequences, lanes along the hidden index so every global access is coalesced;
+// its six input rows per sequence were prefetched with cp.async during the previous step's GEMM),
+// then the [16 x 3H] . [3H x H] product on the FMA pipe with FFMA2, the contraction split in two
+// halves over 2 x 104 threads (thread tile 4 sequences x 4 hidden units).
+#pragma once
+
+#include "wg_common.cuh"
+
+namespace wg {
+
+constexpr int kGbBT = 16;        // sequences per CTA
+constexpr int kGbThreads = 256;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, bool pred) {
+    const int src_bytes = pred ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async8z(void* smem_dst, const void* gmem_src, bool pred) {
+    const int src_bytes = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+
+// HP = H rounded up to 4 (row stride of the per-sequence vectors), GR = 3H rounded up to 8
+// (contraction length, split in two halves of GR / 2, each a multiple of 4).
+__host__ __device__ inline size_t gru_bwd_smem_floats(int HP, int GR) {
+    size_t n = 0;
+    n += (size_t)GR * HP;           // W_hh rows (zero padded)
+    n += (size_t)kGbBT * (GR + 4);  // dgh of the current step
+    n += 3 * (size_t)kGbBT * HP;    // D (g z), P0, P1 (the two halves of dgh . W_hh)
+    n += 6 * (size_t)kGbBT * HP;    // staged inputs of one step: dout, r, z, n, hn, h_prev
+    return n;
+}
+
+__global__ void __launch_bounds__(kGbThreads, 1)
+    gru_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ out, const float* __restrict__ dout,
+                   const float* __restrict__ w_hh, float* __restrict__ DG, float* __restrict__ bias_part,
+                   long long B, int T, int H, int LD4, int HP, int GR) {
+    extern __shared__ __align__(16) float smem[];
+    const int DS = GR + 4;  // dgh row stride: rows 4 apart land in different banks
+    float* Ws = smem;                         // [GR][HP]
+    float* dgh = Ws + (size_t)GR * HP;        // [16][DS]
+    float* Dd = dgh + kGbBT * DS;             // [16][HP]
+    float* P0 = Dd + kGbBT * HP;
+    float* P1 = P0 + kGbBT * HP;
+    float* stg = P1 + kGbBT * HP;             // [6][16][HP]
+
+    const int tid = threadIdx.x;
+    const long long b0 = (long long)blockIdx.x * kGbBT;
+    const int G = 3 * H;
+
+    for (int e = tid; e < GR * HP; e += kGbThreads) {
+        const int n = e / HP, k = e - n * HP;
+        Ws[e] = (n < G && k < H) ? __ldg(w_hh + (size_t)n * H + k) : 0.0f;
+    }
+    for (int e = tid; e < kGbBT * DS; e += kGbThreads) dgh[e] = 0.0f;
+    for (int e = tid; e < 3 * kGbBT * HP; e += kGbThreads) Dd[e] = 0.0f;      // D, P0, P1
+    for (int e = tid; e < 6 * kGbBT * HP; e += kGbThreads) stg[e] = 0.0f;
+
+    // ---- staging of one step's inputs: six H-long rows per sequence ----
+    const bool even = (H & 1) == 0 && (LD4 & 1) == 0;
+    auto prefetch = [&](int t) {
+        const int per_row = even ? (H >> 1) : H;       // copies per row
+        const int total = 6 * kGbBT * per_row;
+        for (int e = tid; e < total; e += kGbThreads) {
+            const int c = e % per_row;
+            const int rb = e / per_row;
+            const int b = rb % kGbBT, q = rb / kGbBT;
+            const bool ok = (b0 + b < B) && !(q == 5 && t == 0);
+            const size_t row = (size_t)(b0 + b) * T + t;
+            const float* src;
+            if (q == 0) src = dout + row * H;
+            else if (q == 5) src = out + (row - 1) * H;      // h_prev = out[b, t - 1]
+            else src = gates + row * LD4 + (size_t)(q - 1) * H;
+            float* dst = stg + ((size_t)q * kGbBT + b) * HP;
+            if (even) cp_async8z(dst + 2 * c, ok ? src + 2 * c : dout, ok);
+            else cp_async4(dst + c, ok ? src + c : dout, ok);
+        }
+        cp_async_commit();
+    };
+
+    __syncthreads();
+    prefetch(T - 1);
+
+    // gate-phase coordinates: hidden unit j (+128 ...) x half of the sequences
+    const int gj = tid & 127;
+    const int gh_ = tid >> 7;              // 0 / 1: sequences [0, 8) / [8, 16)
+    // GEMM coordinates: contraction half kh, row group rg (4 sequences), column group cg (4 units)
+    const int n_cg = HP >> 2;
+    const int per_half = 4 * n_cg;
+    const int kh = tid / per_half;         // >= 2: idle in the GEMM
+    const int rem = tid - kh * per_half;
+    const int rg = rem / n_cg, cg = rem - rg * n_cg;
+    const int KH = GR >> 1;
+
+    // per-thread column sums of DG over this CTA's sequences and all steps (hidden units gj, gj+128, ...)
+    constexpr int kMaxJ = 4;   // H <= 512
+    float bsum[kMaxJ][4];
+#pragma unroll
+    for (int u = 0; u < kMaxJ; ++u) bsum[u][0] = bsum[u][1] = bsum[u][2] = bsum[u][3] = 0.0f;
+
+    for (int t = T - 1; t >= 0; --t) {
+        cp_async_wait<0>();
+        __syncthreads();   // staged inputs of step t and the previous GEMM's P0 / P1 are visible
+
+        // ================= gate phase =================
+#pragma unroll
+        for (int u = 0; u < kMaxJ; ++u) {
+            const int j = gj + u * 128;
+            if (j < H) {
+#pragma unroll
+                for (int bl = 0; bl < kGbBT / 2; ++bl) {
+                    const int b = gh_ * (kGbBT / 2) + bl;
+                    const int o = b * HP + j;
+                    const float g = stg[o] + Dd[o] + P0[o] + P1[o];
+                    const float r = stg[1 * kGbBT * HP + o], z = stg[2 * kGbBT * HP + o];
+                    const float n = stg[3 * kGbBT * HP + o], hn = stg[4 * kGbBT * HP + o];
+                    const float hp = stg[5 * kGbBT * HP + o];
+                    const float dn = g * (1.0f - z);
+                    const float dz = g * (hp - n);
+                    const float da_n = dn * (1.0f - n * n);
+                    const float da_z = dz * z * (1.0f - z);
+                    const float da_r = da_n * hn * r * (1.0f - r);
+                    const float da_nr = da_n * r;
+                    Dd[o] = g * z;
+                    float* d = dgh + b * DS;
+                    d[j] = da_r;
+                    d[H + j] = da_z;
+                    d[2 * H + j] = da_nr;
+                    if (b0 + b < B) {
+                        float* dg = DG + ((size_t)(b0 + b) * T + t) * LD4;
+                        dg[j] = da_r;
+                        dg[H + j] = da_z;
+                        dg[2 * H + j] = da_n;
+                        dg[3 * H + j] = da_nr;
+                    }
+                    bsum[u][0] += da_r; bsum[u][1] += da_z; bsum[u][2] += da_n; bsum[u][3] += da_nr;
+                }
+            }
+        }
+        __syncthreads();   // dgh complete; the staged inputs are free
+        if (t == 0) break;
+        prefetch(t - 1);   // lands during the GEMM
+
+        // ================= P = dgh . W_hh (two contraction halves) =================
+        if (kh < 2) {
+            float2 acc[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.0f, 0.0f);
+            const float* ap = dgh + (rg * 4) * DS + kh * KH;
+            const float* wp = Ws + (size_t)(kh * KH) * HP + cg * 4;
+#pragma unroll 2
+            for (int n = 0; n < KH; n += 4) {
+                float4 a[4], w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(ap + i * DS + n);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(wp + (size_t)(n + kk) * HP);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                        const float2 aa = make_float2(av, av);
+                        acc[i][0] = __ffma2_rn(aa, make_float2(w[kk].x, w[kk].y), acc[i][0]);
+                        acc[i][1] = __ffma2_rn(aa, make_float2(w[kk].z, w[kk].w), acc[i][1]);
+                    }
+                }
+            }
+            float* P = kh == 0 ? P0 : P1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(P + (rg * 4 + i) * HP + cg * 4) =
+                    make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
+        }
+    }
+
+    // ---- per-CTA column sums of DG: bias_part[(cta * 2 + half)][LD4] ----
+    float* bp = bias_part + ((size_t)blockIdx.x * 2 + gh_) * LD4;
+#pragma unroll
+    for (int u = 0; u < kMaxJ; ++u) {
+        const int j = gj + u * 128;
+        if (j < H) {
+            bp[j] = bsum[u][0];
+            bp[H + j] = bsum[u][1];
+            bp[2 * H + j] = bsum[u][2];
+            bp[3 * H + j] = bsum[u][3];
+        }
+    }
+}
+
+// db_ih = [sum da_r | sum da_z | sum da_n], db_hh = [sum da_r | sum da_z | sum da_n r], summed over
+// the per-CTA partials in a fixed order.
+__global__ void gru_bias_grad_kernel(const float* __restrict__ part, int nparts, int H, int LD4,
+                                     float* __restrict__ db_ih, float* __restrict__ db_hh) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 4 * H) return;
+    float s = 0.0f;
+    for (int z = 0; z < nparts; ++z) s += part[(size_t)z * LD4 + c];
+    if (c < 2 * H) {
+        db_ih[c] = s;
+        db_hh[c] = s;
+    } else if (c < 3 * H) {
+        db_ih[c] = s;
+    } else {
+        db_hh[c - H] = s;
+    }
+}
+
+}  // namespace wg

@@ -85,11 +85,13 @@ struct RcFrag {
     float2 wc[4];     // W[k + kk][cC .. cC+1]
 };
 
-template <int NWARPS, bool W_SMEM>
+// SAVE (training forward): the gate values the backward pass needs are written beside h:
+// gsave[b, t, :] = [r | z | n | hn] with hn = W_hn h + b_hn, row stride ldsave (gru_bwd.cuh).
+template <int NWARPS, bool W_SMEM, bool SAVE = false>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
     gru_recur_kernel(const float* __restrict__ GI, const float* __restrict__ WhT,
                      const float* __restrict__ bhn, float* __restrict__ out, long long B, int T, int H,
-                     int ldg, int KP, int NP, int TS) {
+                     int ldg, int KP, int NP, int TS, float* __restrict__ gsave = nullptr, int ldsave = 0) {
     constexpr int NT = NWARPS * 32;
     constexpr int WG = NWARPS / 2;   // warps per group
     constexpr int NG = WG * 32;      // threads per group
@@ -334,8 +336,16 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
             for (int bl = 0; bl < GB; ++bl) {
                 const float r = sigmoid_f(g[bl * ldg]);
                 const float z = sigmoid_f(g[bl * ldg + H]);
-                const float n = tanh_f(g[bl * ldg + H2] + r * (gn[bl * KP] + bn));
+                const float hn = gn[bl * KP] + bn;
+                const float n = tanh_f(g[bl * ldg + H2] + r * hn);
                 hnew[bl] = (hp[bl * RS] - n) * z + n;
+                if (SAVE && b0 + grp * GB + bl < B) {
+                    float* gs = gsave + ((size_t)(b0 + grp * GB + bl) * T + t) * ldsave + j;
+                    gs[0] = r;
+                    gs[H] = z;
+                    gs[H2] = n;
+                    gs[H2 + H] = hn;
+                }
             }
 #pragma unroll
             for (int bl = 0; bl < GB; ++bl) {

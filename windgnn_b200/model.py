@@ -69,6 +69,12 @@ class GCN_GRU(nn.Module):
             if self._csr_cache is None or self._csr_cache[0] != key:
                 self._csr_cache = (key, ops.dense_to_csr(adj_matrix))
             out = ops.gcn_gru_forward_csr(*self._csr_cache[1], attr_matrix, *params, self.chunk)
+        elif torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            # training (main.py:66 runs with grad enabled): forward that saves the gate values, library
+            # backward (train.py); FP32 path only
+            from .train import GcnGruFunction
+
+            out = GcnGruFunction.apply(adj_matrix, attr_matrix, *params)
         else:
             out = ops.gcn_gru_forward(adj_matrix, attr_matrix, *params, self.chunk, self._flags())
         return out.squeeze(0)  # step6:26 — a no-op unless B == 1
