@@ -226,6 +226,9 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3"],
                     help="fp32: every contraction as FP32 FMA; tf32x3: GRU input projection on tcgen05 (3xTF32)")
     ap.add_argument("--ref-seqs", type=int, default=512, help="sequences per step of the reference arm's sample")
+    ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=512,
+                    help="windows per GPU of the training-step measurement (BASELINE.json configs[4]: 4096 over 8 GPUs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -319,6 +322,38 @@ def main():
                            "max_abs_diff_vs_fp32_path_normalised": err, "parity_bar": 1e-5}
         finally:
             model.precision = args.precision
+    barrier()
+
+    # ---------------- training step (BASELINE.json configs[4]): fwd + MSE + bwd + all-reduce + Adam ----------
+    train_step = None
+    if not args.no_train_step:
+        from windgnn_b200 import train as wtrain
+
+        tmodel = windgnn_b200.GCN_GRU(F, F, F, I, H)
+        tmodel.load_state_dict(sd, strict=True)
+        tmodel = tmodel.to(dev).train()
+        trainer = wtrain.Trainer(tmodel, adj, lr=1e-3)   # main.py:45,52
+        Bt = args.train_batch
+        xt = x[:Bt] if Bt <= Bg else torch.rand((Bt, T, S, F), generator=gen, device=dev)
+        yt_ = torch.rand((Bt, T, H), generator=gen, device=dev)
+        for _ in range(warmup):
+            trainer.step(xt, yt_)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(steps):
+            tl = trainer.step(xt, yt_)
+        a1.record()
+        barrier()
+        ms_tr = max_over_ranks(a0.elapsed_time(a1))
+        train_step = {"metric": "gcn_gru_train_step_sequences_per_s", "value": world * Bt * steps / (ms_tr * 1e-3),
+                      "unit": UNIT, "ms_per_step": ms_tr / steps, "batch_per_gpu": Bt, "global_batch": Bt * world,
+                      "loss_after": float(tl.item()),
+                      "what": "forward (gates saved) + MSE + BPTT/GEMM/GCN backward + "
+                              + ("NCCL sum all-reduce of one flat 167,440-float gradient bucket + " if world > 1 else "")
+                              + "fused Adam, all inside the timed region; FP32",
+                      "gpu_launches_per_step": 21 + (1 if world > 1 else 0)}
+        del trainer, tmodel, xt, yt_
     barrier()
 
     # ---------------- per-kernel timing for the roofline (rank 0's GPU, same stream) -------------
@@ -427,7 +462,7 @@ def main():
                        "l2_policy": "inputs (1.22 GB per step) larger than L2",
                        "station_sequence_predictions_per_s": value * S},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * steps,
-            "roofline": roofline, "cpu_baseline": cpu, "tensor_path": tensor_path,
+            "roofline": roofline, "cpu_baseline": cpu, "tensor_path": tensor_path, "train_step": train_step,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

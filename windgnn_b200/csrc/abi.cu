@@ -949,7 +949,8 @@ int wg_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp
     const long long blocks = (n + 255) / 256;
     const unsigned grid = (unsigned)(blocks < 8LL * wg::kNumSMs ? blocks : 8LL * wg::kNumSMs);
     wg::adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        param, grad, exp_avg, exp_avg_sq, n, (float)grad_scale, (float)beta1, (float)beta2, (float)(lr / bc1),
+        param, grad, exp_avg, exp_avg_sq, n, (float)grad_scale, (float)beta1, (float)beta2, (float)(1.0 - beta1),
+        (float)(1.0 - beta2), (float)(lr / bc1),
         (float)sqrt(bc2), (float)eps);
     WG_CUDA(cudaGetLastError());
     return WG_OK;

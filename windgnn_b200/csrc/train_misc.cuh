@@ -47,12 +47,12 @@ __global__ void mse_finish_kernel(const double* __restrict__ partial, int nparts
 //   p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)          bc = 1 - beta^step (host, fp64)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float grad_scale, float beta1, float beta2,
-                            float step_size, float sqrt_bc2, float eps) {
+                            float omb1, float omb2, float step_size, float sqrt_bc2, float eps) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
          e += (long long)gridDim.x * blockDim.x) {
         const float gg = g[e] * grad_scale;
-        const float mm = beta1 * m[e] + (1.0f - beta1) * gg;
-        const float vv = beta2 * v[e] + (1.0f - beta2) * gg * gg;
+        const float mm = beta1 * m[e] + omb1 * gg;   // omb = 1 - beta, rounded once from fp64 like torch
+        const float vv = beta2 * v[e] + omb2 * gg * gg;
         m[e] = mm;
         v[e] = vv;
         const float denom = sqrtf(vv) / sqrt_bc2 + eps;
