@@ -426,7 +426,7 @@ struct TrainPlan {
 
 int pick_splits(long long M, long long N, long long K) {
     const long long tiles = ((M + wg::kSgBM - 1) / wg::kSgBM) * ((N + wg::kSgBN - 1) / wg::kSgBN);
-    long long s = (2LL * wg::kNumSMs + tiles - 1) / tiles;
+    long long s = (2LL * wg::kNumSMs) / tiles;  // whole grid resident at once (2 CTAs per SM): one wave
     const long long kmax = (K + 63) / 64;  // at least 64 k's per split
     if (s > kmax) s = kmax;
     return s < 1 ? 1 : (int)s;
@@ -451,18 +451,17 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
     tp.rows = (B > 0 ? B : 1) * (long long)T;
     tp.grid_gb = (int)(((B > 0 ? B : 1) + wg::kGbBT - 1) / wg::kGbBT);
     // GCN backward geometry (same station grouping as the forward)
-    tp.sg_gcn = pick_sg(S);
+    // 4 stations per thread: the slabs bound the CTA to ~24 rows, so the narrower station group is what
+    // puts 7 warps instead of 4 on the SM
+    tp.sg_gcn = 4;
     tp.fp_gcn = (Fi == 13 && Fh == 13 && Fo == 13) ? 13 : 16;
-    if (tp.fp_gcn == 16) tp.sg_gcn = 4;
     const int NSG = wg::ceil_div(S, tp.sg_gcn);
     if (NSG > wg::kGcnThreads) return fail(WG_ERR_UNSUPPORTED, "training: S=%d too large for the dense GCN kernels", S);
-    int RB = wg::kGcnThreads / NSG;
+    int RB = wg::kGbwThreads / NSG;
     const int cols = S * Fi, dcols = S * Fo;
     const int need = ((cols % 4 == 0) && (dcols % 4 == 0)) ? 1 : ((cols % 2 == 0) && (dcols % 2 == 0)) ? 2 : 4;
     if (RB > need) RB -= RB % need;
-    auto smem_of = [&](int rb) {
-        return (tp.sg_gcn == 7 ? wg::gcn_bwd_smem_floats<7>(S, Fo, rb) : wg::gcn_bwd_smem_floats<4>(S, Fo, rb)) * 4;
-    };
+    auto smem_of = [&](int rb) { return wg::gcn_bwd_smem_floats<4>(S, Fo, rb) * 4; };
     while (smem_of(RB) > (size_t)wg::kMaxSmemOptin && RB > 1) RB = (RB > need) ? RB - need : RB - 1;
     if (smem_of(RB) > (size_t)wg::kMaxSmemOptin)
         return fail(WG_ERR_UNSUPPORTED, "training: S=%d does not fit the shared-memory GCN backward", S);
@@ -478,7 +477,7 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
     tp.off_dg = o;    o = align_up(o + (size_t)tp.rows * tp.LD4 * 4);
     tp.off_du = o;    o = align_up(o + (size_t)tp.rows * p.I * 4);
     tp.off_biasp = o; o = align_up(o + (size_t)tp.grid_gb * 2 * tp.LD4 * 4);
-    tp.off_gcnp = o;  o = align_up(o + (size_t)tp.grid_gcn * (wg::kGcnThreads / 16) * (2 * 256 + 32) * 4);
+    tp.off_gcnp = o;  o = align_up(o + (size_t)tp.grid_gcn * (wg::kGbwThreads / 16) * (2 * 256 + 32) * 4);
     size_t sk = (size_t)tp.splits_hh_a * 2 * H * H;
     if ((size_t)tp.splits_hh_b * H * H > sk) sk = (size_t)tp.splits_hh_b * H * H;
     if ((size_t)tp.splits_ih * p.I * p.G > sk) sk = (size_t)tp.splits_ih * p.I * p.G;
@@ -514,7 +513,7 @@ int launch_gcn_bwd_t(const TrainPlan& tp, void* ws, const float* x, const float*
     const Plan& p = tp.f;
     auto kern = wg::gcn_bwd_kernel<FP, SG>;
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_gcn));
-    kern<<<tp.grid_gcn, wg::kGcnThreads, tp.smem_gcn, st>>>(x, ws_ptr<float>(ws, tp.off_du), adj, w1, b1, w2, b2,
+    kern<<<tp.grid_gcn, wg::kGbwThreads, tp.smem_gcn, st>>>(x, ws_ptr<float>(ws, tp.off_du), adj, w1, b1, w2, b2,
                                                            ws_ptr<float>(ws, tp.off_gcnp), tp.rows, p.S, p.Fi, p.Fh,
                                                            p.Fo, tp.rb_gcn);
     WG_CUDA(cudaGetLastError());
@@ -906,12 +905,11 @@ int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, c
         WG_CUDA(cudaGetLastError());
     }
     // 5. GCN backward: dW1, db1, dW2, db2
-    if (tp.fp_gcn == 13 && tp.sg_gcn == 7) rc = launch_gcn_bwd_t<13, 7>(tp, workspace, x, adj, w1, b1, w2, b2, st);
-    else if (tp.fp_gcn == 13) rc = launch_gcn_bwd_t<13, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
+    if (tp.fp_gcn == 13) rc = launch_gcn_bwd_t<13, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
     else rc = launch_gcn_bwd_t<16, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
     if (rc) return rc;
     wg::gcn_bwd_finish_kernel<<<(2 * 256 + 32 + 127) / 128, 128, 0, st>>>(
-        ws_ptr<float>(workspace, tp.off_gcnp), tp.grid_gcn * (wg::kGcnThreads / 16), F_in, F_hid, F_out, d_w1, d_b1,
+        ws_ptr<float>(workspace, tp.off_gcnp), tp.grid_gcn * (wg::kGbwThreads / 16), F_in, F_hid, F_out, d_w1, d_b1,
         d_w2, d_b2);
     WG_CUDA(cudaGetLastError());
     return WG_OK;

@@ -26,6 +26,9 @@
 namespace wg {
 
 constexpr int kGbwFS = 16;  // floats per station in the padded slabs
+constexpr int kGbwThreads = 256;
+// padded slab row stride: + 4 floats so that the rows a warp touches at once start in different banks
+__host__ __device__ inline int gcn_bwd_row_stride(int S) { return S * kGbwFS + 4; }
 
 template <int SG>
 __host__ __device__ inline size_t gcn_bwd_smem_floats(int S, int Fo, int RB) {
@@ -34,7 +37,7 @@ __host__ __device__ inline size_t gcn_bwd_smem_floats(int S, int Fo, int RB) {
     n += 2 * (size_t)S * NSG * 8;          // adjT (A[own][sp]) and adjN (A[sp][own])
     n += 3 * (size_t)kGbwFS * kGbwFS;      // W1, W2, W2^T (zero padded 16 x 16)
     n += 2 * (size_t)kGbwFS;               // b1, b2
-    n += 3 * (size_t)RB * S * kGbwFS;      // padded slabs b0, b1, b2
+    n += 3 * (size_t)RB * gcn_bwd_row_stride(S);  // padded slabs s0, s1, s2
     n += (size_t)round_up(RB * S * Fo, 4); // dense dU block
     n += 4;                                // mbarrier
     return n;
@@ -42,7 +45,8 @@ __host__ __device__ inline size_t gcn_bwd_smem_floats(int S, int Fo, int RB) {
 
 // acc[i][fp] = sum_sp tab[sp][q][i] * (x[sp][2fp], x[sp][2fp+1]); x rows `stride` floats apart,
 // features >= flim read as zero (dense input slab) or are zero padding (stride 16 slabs).
-template <int FPP, int SG>
+// VEC: the slab is a padded one (16 floats per station, 16-byte aligned): features come by LDS.128.
+template <int FPP, int SG, bool VEC>
 __device__ __forceinline__ void gcn_bwd_agg(float2 (&acc)[SG][FPP], const float* __restrict__ xrow, int stride,
                                             int flim, const float* __restrict__ arow, int astride, int S) {
 #pragma unroll
@@ -60,9 +64,19 @@ __device__ __forceinline__ void gcn_bwd_agg(float2 (&acc)[SG][FPP], const float*
                 a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
             }
         }
-        float x[2 * FPP];
+        float x[2 * FPP + 2];
+        if (VEC) {
 #pragma unroll
-        for (int f = 0; f < 2 * FPP; ++f) x[f] = f < flim ? xrow[sp * stride + f] : 0.0f;
+            for (int v = 0; v < (2 * FPP + 3) / 4; ++v) {
+                const float4 t = *reinterpret_cast<const float4*>(xrow + sp * kGbwFS + 4 * v);
+                x[4 * v] = t.x;
+                x[4 * v + 1] = t.y;
+                if (4 * v + 2 < 2 * FPP) { x[4 * v + 2] = t.z; x[4 * v + 3] = t.w; }
+            }
+        } else {
+#pragma unroll
+            for (int f = 0; f < 2 * FPP; ++f) x[f] = f < flim ? xrow[sp * stride + f] : 0.0f;
+        }
 #pragma unroll
         for (int i = 0; i < SG; ++i) {
             const float2 aa = make_float2(a[i], a[i]);
@@ -94,7 +108,7 @@ __device__ __forceinline__ void gcn_bwd_xform4(float2 (&o)[SG][2], const float2 
 // FP: compile-time bound on the feature widths (13 for the reference's models, else 16).
 // part: [gridDim.x * 8][2 * 256 + 32] per-thread-slice partials (dW1 16x16, dW2 16x16, db1 16, db2 16).
 template <int FP, int SG>
-__global__ void __launch_bounds__(kGcnThreads, 1)
+__global__ void __launch_bounds__(kGbwThreads, 1)
     gcn_bwd_kernel(const float* __restrict__ X, const float* __restrict__ dU, const float* __restrict__ adj,
                    const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                    const float* __restrict__ b2, float* __restrict__ part, long long R, int S, int Fi, int Fh,
@@ -104,7 +118,7 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
     const int NSG = ceil_div(S, SG);
     const int tid = threadIdx.x;
     const int astride = NSG * 8;
-    const int SR = S * kGbwFS;   // padded slab row stride
+    const int SR = gcn_bwd_row_stride(S);   // padded slab row stride
 
     float* adjT = smem;
     float* adjN = adjT + (size_t)S * NSG * 8;
@@ -119,7 +133,7 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
     float* sd = s2 + (size_t)RB * SR;          // dU (dense)
     uint64_t* bar = reinterpret_cast<uint64_t*>(sd + round_up(RB * S * Fo, 4));
 
-    for (int e = tid; e < S * NSG * 8; e += kGcnThreads) {
+    for (int e = tid; e < S * NSG * 8; e += kGbwThreads) {
         const int sp = e / (NSG * 8);
         const int c = e % (NSG * 8);
         const int qq = c >> 3, i = c & 7;
@@ -128,13 +142,13 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
         adjT[e] = ok ? adj[(size_t)s * S + sp] : 0.0f;
         adjN[e] = ok ? adj[(size_t)sp * S + s] : 0.0f;
     }
-    for (int e = tid; e < kGbwFS * kGbwFS; e += kGcnThreads) {
+    for (int e = tid; e < kGbwFS * kGbwFS; e += kGbwThreads) {
         const int f = e / kGbwFS, fo = e % kGbwFS;
         w1d[e] = (f < Fi && fo < Fh) ? W1[f * Fh + fo] : 0.0f;
         w2d[e] = (f < Fh && fo < Fo) ? W2[f * Fo + fo] : 0.0f;
         w2t[e] = (f < Fo && fo < Fh) ? W2[fo * Fo + f] : 0.0f;   // w2t[fo'][f'] = W2[f'][fo']
     }
-    for (int e = tid; e < kGbwFS; e += kGcnThreads) {
+    for (int e = tid; e < kGbwFS; e += kGbwThreads) {
         b1s[e] = e < Fh ? b1[e] : 0.0f;
         b2s[e] = e < Fo ? b2[e] : 0.0f;
     }
@@ -157,24 +171,27 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
 #pragma unroll
     for (int i = 0; i < 4; ++i) aw1[i][0] = aw1[i][1] = aw2[i][0] = aw2[i][1] = make_float2(0.0f, 0.0f);
 
-    auto reduce = [&](const float* __restrict__ sa, const float* __restrict__ sb, int kn, float2 (&aw)[4][2],
+    // sum over the block's (row, station) pairs: this thread takes stations ks, ks + 8, ... of every row
+    auto reduce = [&](const float* __restrict__ sa, const float* __restrict__ sb, int nrows_, float2 (&aw)[4][2],
                       float4& ab) {
-        const float* pa = sa + fi * 4;
-        const float* pb = sb + fj * 4;
+        for (int row = 0; row < nrows_; ++row) {
+            const float* pa = sa + (size_t)row * SR + fi * 4;
+            const float* pb = sb + (size_t)row * SR + fj * 4;
 #pragma unroll 2
-        for (int k = ks; k < kn; k += kGcnThreads / 16) {
-            const float4 a = *reinterpret_cast<const float4*>(pa + k * kGbwFS);
-            const float4 b = *reinterpret_cast<const float4*>(pb + k * kGbwFS);
-            const float2 blo = make_float2(b.x, b.y), bhi = make_float2(b.z, b.w);
-            aw[0][0] = __ffma2_rn(make_float2(a.x, a.x), blo, aw[0][0]);
-            aw[0][1] = __ffma2_rn(make_float2(a.x, a.x), bhi, aw[0][1]);
-            aw[1][0] = __ffma2_rn(make_float2(a.y, a.y), blo, aw[1][0]);
-            aw[1][1] = __ffma2_rn(make_float2(a.y, a.y), bhi, aw[1][1]);
-            aw[2][0] = __ffma2_rn(make_float2(a.z, a.z), blo, aw[2][0]);
-            aw[2][1] = __ffma2_rn(make_float2(a.z, a.z), bhi, aw[2][1]);
-            aw[3][0] = __ffma2_rn(make_float2(a.w, a.w), blo, aw[3][0]);
-            aw[3][1] = __ffma2_rn(make_float2(a.w, a.w), bhi, aw[3][1]);
-            if (fi == 0) { ab.x += b.x; ab.y += b.y; ab.z += b.z; ab.w += b.w; }
+            for (int k = ks; k < S; k += kGbwThreads / 16) {
+                const float4 a = *reinterpret_cast<const float4*>(pa + k * kGbwFS);
+                const float4 b = *reinterpret_cast<const float4*>(pb + k * kGbwFS);
+                const float2 blo = make_float2(b.x, b.y), bhi = make_float2(b.z, b.w);
+                aw[0][0] = __ffma2_rn(make_float2(a.x, a.x), blo, aw[0][0]);
+                aw[0][1] = __ffma2_rn(make_float2(a.x, a.x), bhi, aw[0][1]);
+                aw[1][0] = __ffma2_rn(make_float2(a.y, a.y), blo, aw[1][0]);
+                aw[1][1] = __ffma2_rn(make_float2(a.y, a.y), bhi, aw[1][1]);
+                aw[2][0] = __ffma2_rn(make_float2(a.z, a.z), blo, aw[2][0]);
+                aw[2][1] = __ffma2_rn(make_float2(a.z, a.z), bhi, aw[2][1]);
+                aw[3][0] = __ffma2_rn(make_float2(a.w, a.w), blo, aw[3][0]);
+                aw[3][1] = __ffma2_rn(make_float2(a.w, a.w), bhi, aw[3][1]);
+                if (fi == 0) { ab.x += b.x; ab.y += b.y; ab.z += b.z; ab.w += b.w; }
+            }
         }
     };
 
@@ -195,18 +212,17 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
             mbar_wait(bar, phase);
             phase ^= 1;
         } else {
-            for (int e = tid; e < nrows * in_cols; e += kGcnThreads) s0[e] = __ldg(xsrc + e);
-            for (int e = tid; e < nrows * du_cols; e += kGcnThreads) sd[e] = __ldg(dsrc + e);
+            for (int e = tid; e < nrows * in_cols; e += kGbwThreads) s0[e] = __ldg(xsrc + e);
+            for (int e = tid; e < nrows * du_cols; e += kGbwThreads) sd[e] = __ldg(dsrc + e);
             __syncthreads();
         }
         const bool active = row_local < nrows && tid < RB * NSG;
-        const int kn = nrows * S;
         unsigned mask1[SG];
         float2 acc[SG][FPP];
 
         // ---- P1: AX = A.X (own stations) ; G1 = relu(AX.W1 + b1) ----
         if (active)
-            gcn_bwd_agg<FPP, SG>(acc, s0 + (size_t)row_local * in_cols, Fi, Fi, adjT + q * 8, astride, S);
+            gcn_bwd_agg<FPP, SG, false>(acc, s0 + (size_t)row_local * in_cols, Fi, Fi, adjT + q * 8, astride, S);
         __syncthreads();   // every read of the dense X block is done: s0 becomes the padded AX slab
         if (active) {
 #pragma unroll
@@ -244,7 +260,7 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
 
         // ---- P2: AG = A.G1 ; dZ2 = dU * [AG.W2 + b2 > 0] ----
         if (active)
-            gcn_bwd_agg<FPP, SG>(acc, s1 + (size_t)row_local * SR, kGbwFS, 2 * FPP, adjT + q * 8, astride, S);
+            gcn_bwd_agg<FPP, SG, true>(acc, s1 + (size_t)row_local * SR, kGbwFS, 2 * FPP, adjT + q * 8, astride, S);
         __syncthreads();   // every read of G1 is done: s1 becomes AG
         if (active) {
 #pragma unroll
@@ -280,7 +296,7 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
         __syncthreads();
 
         // ---- P3: dW2 += AG^T dZ2, db2 += colsum(dZ2) ; then dAG = dZ2 . W2^T in place ----
-        reduce(s1, s2, kn, aw2, ab2);
+        reduce(s1, s2, nrows, aw2, ab2);
         if (active) {   // own dZ2 rows into registers (reads only) before anyone overwrites s2
 #pragma unroll
             for (int i = 0; i < SG; ++i) {
@@ -309,7 +325,7 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
 
         // ---- P4: dG1 = A^T dAG ; dZ1 = dG1 * [G1 > 0] -> s1 ----
         if (active) {
-            gcn_bwd_agg<FPP, SG>(acc, s2 + (size_t)row_local * SR, kGbwFS, 2 * FPP, adjN + q * 8, astride, S);
+            gcn_bwd_agg<FPP, SG, true>(acc, s2 + (size_t)row_local * SR, kGbwFS, 2 * FPP, adjN + q * 8, astride, S);
 #pragma unroll
             for (int i = 0; i < SG; ++i) {
                 const int s = q * SG + i;
@@ -330,12 +346,12 @@ __global__ void __launch_bounds__(kGcnThreads, 1)
         __syncthreads();
 
         // ---- P5: dW1 += AX^T dZ1, db1 += colsum(dZ1) ----
-        reduce(s0, s1, kn, aw1, ab1);
+        reduce(s0, s1, nrows, aw1, ab1);
         __syncthreads();   // the slabs are free for the next block's bulk copies
     }
 
     // ---- per-thread partials: part[(cta * 8 + ks)][...] ----
-    float* pp = part + ((size_t)blockIdx.x * (kGcnThreads / 16) + ks) * (2 * 256 + 32);
+    float* pp = part + ((size_t)blockIdx.x * (kGbwThreads / 16) + ks) * (2 * 256 + 32);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int f = fi * 4 + i;

@@ -76,23 +76,28 @@ __global__ void __launch_bounds__(kGbThreads, 1)
     for (int e = tid; e < 6 * kGbBT * HP; e += kGbThreads) stg[e] = 0.0f;
 
     // ---- staging of one step's inputs: six H-long rows per sequence ----
-    const bool even = (H & 1) == 0 && (LD4 & 1) == 0;
+    const bool even = (H & 1) == 0 && (LD4 & 1) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(gates) | reinterpret_cast<uintptr_t>(out) |
+                        reinterpret_cast<uintptr_t>(dout)) & 7) == 0;
+    // a warp takes (input, sequence) rows w, w + 8, ...; its lanes walk the row (no divisions)
     auto prefetch = [&](int t) {
         const int per_row = even ? (H >> 1) : H;       // copies per row
-        const int total = 6 * kGbBT * per_row;
-        for (int e = tid; e < total; e += kGbThreads) {
-            const int c = e % per_row;
-            const int rb = e / per_row;
+        for (int rb = tid >> 5; rb < 6 * kGbBT; rb += kGbThreads / 32) {
             const int b = rb % kGbBT, q = rb / kGbBT;
             const bool ok = (b0 + b < B) && !(q == 5 && t == 0);
             const size_t row = (size_t)(b0 + b) * T + t;
-            const float* src;
-            if (q == 0) src = dout + row * H;
-            else if (q == 5) src = out + (row - 1) * H;      // h_prev = out[b, t - 1]
-            else src = gates + row * LD4 + (size_t)(q - 1) * H;
+            const float* src = dout;                         // any valid address when !ok (zero fill)
+            if (ok) {
+                if (q == 0) src = dout + row * H;
+                else if (q == 5) src = out + (row - 1) * H;  // h_prev = out[b, t - 1]
+                else src = gates + row * LD4 + (size_t)(q - 1) * H;
+            }
             float* dst = stg + ((size_t)q * kGbBT + b) * HP;
-            if (even) cp_async8z(dst + 2 * c, ok ? src + 2 * c : dout, ok);
-            else cp_async4(dst + c, ok ? src + c : dout, ok);
+            if (even) {
+                for (int c = tid & 31; c < per_row; c += 32) cp_async8z(dst + 2 * c, ok ? src + 2 * c : src, ok);
+            } else {
+                for (int c = tid & 31; c < per_row; c += 32) cp_async4(dst + c, ok ? src + c : src, ok);
+            }
         }
         cp_async_commit();
     };
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(kGbThreads, 1)
     const int KH = GR >> 1;
 
     // per-thread column sums of DG over this CTA's sequences and all steps (hidden units gj, gj+128, ...)
-    constexpr int kMaxJ = 4;   // H <= 512
+    constexpr int kMaxJ = 1;   // H <= 128 (the launcher enforces HP <= 128)
     float bsum[kMaxJ][4];
 #pragma unroll
     for (int u = 0; u < kMaxJ; ++u) bsum[u][0] = bsum[u][1] = bsum[u][2] = bsum[u][3] = 0.0f;
