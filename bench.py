@@ -213,6 +213,107 @@ def run_reference(args, rank: int):
     }), flush=True)
 
 
+def run_scaled(args, rank: int, world: int, local_rank: int):
+    """The two scaled BASELINE configs (device-resident throughput only; parity for both shapes is in
+    tests/test_parity_gpu.py).  fwd34_1m: 2^20 windows in total, rank r owns a contiguous 1/world of them and
+    streams them through the library in resident pieces of <= 131072 windows (38.9 GB of input each; one
+    synthetic piece is generated on the device and reused for every piece of the shard).  fwd4096: 256 windows
+    per GPU of the 4096-station kNN graph (weak scaling)."""
+    import windgnn_b200
+    from windgnn_b200.shard import max_over_ranks, shard_range
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    warmup, steps = max(args.warmup, 3), max(args.steps, 1)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    if args.workload == "fwd34_1m":
+        sd, latlon = load_workload()
+        model = windgnn_b200.GCN_GRU(F, F, F, I, H)
+        model.load_state_dict(sd, strict=True)
+        adj = windgnn_b200.build_graph_from_latlon(latlon, device=dev, dtype=torch.float32)
+        total = 1 << 20
+        lo, hi = shard_range(total, rank, world)
+        piece = min(hi - lo, 131072)
+        n_pieces = (hi - lo + piece - 1) // piece
+        x = torch.rand((piece, T, S, F), generator=gen, device=dev)
+        Sx, Tx, flop_seq, bytes_seq, scaling = S, T, FLOP_PER_SEQ, BYTES_PER_SEQ, "strong"
+        units = total
+        name = ("34-station GCN-GRU forward (wind_gnn_34.pth), T=168, 2^20 windows sharded contiguously over the "
+                f"GPUs, {n_pieces} resident piece(s) of {piece} per GPU (BASELINE.json configs[2])")
+
+        def step():
+            for _ in range(n_pieces):
+                model(adj, x)
+    else:
+        S4, Fh4, H4, T4, B4 = 4096, 128, 128, 24, args.batch if args.batch != B_PER_GPU else 256
+        torch.manual_seed(4)
+        model = windgnn_b200.GCN_GRU(F, Fh4, F, F * S4, H4)
+        with torch.no_grad():
+            model.conv1.weight.mul_(0.05)
+            model.conv2.weight.mul_(0.05)
+        ll = windgnn_b200.synthetic_coordinates(S4, seed=0, device=dev).cpu().numpy()
+        adj = windgnn_b200.knn_graph_from_latlon(ll, k=8, device=dev)
+        nnz = int((adj != 0).sum().item())
+        x = torch.rand((B4, T4, S4, F), generator=gen, device=dev)
+        Sx, Tx, scaling = S4, T4, "weak"
+        flop_seq = T4 * (2 * (nnz * F + S4 * F * Fh4) + 2 * (nnz * Fh4 + S4 * Fh4 * F) + 2 * (F * S4) * 3 * H4
+                         + 2 * H4 * 3 * H4)
+        bytes_seq = T4 * S4 * F * 4 + T4 * H4 * 4
+        units = world * B4
+        name = (f"synthetic 4096-station kNN(k=8) graph (nnz {nnz}), GCN_GRU(13,128,13,53248,128), T=24, "
+                f"{B4} windows per GPU (BASELINE.json configs[3], SURVEY 8(d) variant C)")
+
+        def step():
+            model(adj, x)
+    model = model.to(dev).eval()
+    with torch.no_grad():
+        for _ in range(warmup):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            barrier()
+            clocks.mark_start()
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            barrier()
+            clocks.mark_stop()
+        ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    if rank == 0:
+        value = units * steps / (ms * 1e-3)
+        lib_peak = windgnn_b200._lib.load().wg_measure_ffma_tflops(local_rank, 10)
+        tfl = flop_seq * value / world / 1e12
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "S": Sx, "T": Tx, "l2_policy": "inputs larger than L2",
+                       "station_sequence_predictions_per_s": value * Sx},
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "fp32", "achieved": tfl, "peak": lib_peak, "unit": "TFLOP/s", "frac": tfl / lib_peak,
+                         "scope": "whole path, per GPU, algorithmic FLOPs", "flop_per_seq": flop_seq,
+                         "hbm_gbs_algorithmic": bytes_seq * value / world / 1e9},
+        }), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,6 +327,10 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3"],
                     help="fp32: every contraction as FP32 FMA; tf32x3: GRU input projection on tcgen05 (3xTF32)")
     ap.add_argument("--ref-seqs", type=int, default=512, help="sequences per step of the reference arm's sample")
+    ap.add_argument("--workload", default="fwd34", choices=["fwd34", "fwd34_1m", "fwd4096"],
+                    help="fwd34: BASELINE configs[1] (default, the contract line); fwd34_1m: configs[2], 2^20 sequences "
+                         "of T=168 sharded over the GPUs (strong scaling); fwd4096: configs[3], 4096-station kNN(8) "
+                         "graph, GCN hidden 128, GRU hidden 128, T=24")
     ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--train-batch", type=int, default=512,
                     help="windows per GPU of the training-step measurement (BASELINE.json configs[4]: 4096 over 8 GPUs)")
@@ -241,6 +346,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — windgnn_b200 has no CPU fallback")
+    if args.workload != "fwd34":
+        run_scaled(args, rank, world, local_rank)
+        return
     import windgnn_b200
     from windgnn_b200 import _lib
 

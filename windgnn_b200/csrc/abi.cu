@@ -262,6 +262,19 @@ int launch_gcn_sparse(const Plan& p, void* ws, const Csr& g, const float* x, con
                       const float* w2, const float* b2, long long rows, cudaStream_t st) {
     if (p.Fi > wg::kSpF || p.Fo > wg::kSpF)
         return fail(WG_ERR_UNSUPPORTED, "sparse GCN: F_in / F_out must be <= %d (got %d / %d)", wg::kSpF, p.Fi, p.Fo);
+    // a whole row's [S, F] slab fits shared memory: the row-resident fused kernel
+    const size_t smem_row = wg::gcn_sparse_row_smem_bytes(p.S, p.Fi, p.Fh, p.Fo);
+    if (smem_row <= (size_t)wg::kMaxSmemOptin && rows >= 1) {
+        auto kern = (p.Fi <= 13 && p.Fo <= 13) ? wg::gcn_sparse_row_kernel<13> : wg::gcn_sparse_row_kernel<16>;
+        WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+        const unsigned grid = (unsigned)(rows < wg::kNumSMs ? rows : wg::kNumSMs);
+        // off_z holds rows * S * F_out floats: its first gridDim rows serve as the per-CTA scratch rows
+        kern<<<grid, wg::kSrThreads, smem_row, st>>>(
+            x, g.rowptr, g.colidx, g.vals, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_z), ws_ptr<float>(ws, p.off_u), rows,
+            p.S, p.Fi, p.Fh, p.Fo, p.IP);
+        WG_CUDA(cudaGetLastError());
+        return WG_OK;
+    }
     const size_t smem = ((size_t)2 * p.Fh * wg::kSpF + p.Fh) * 4;
     if (smem > (size_t)wg::kMaxSmemOptin)
         return fail(WG_ERR_UNSUPPORTED, "sparse GCN: hidden width %d too large", p.Fh);
