@@ -123,7 +123,8 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     p.off_u = o;    o = align_up(o + rows_tiled * p.IP * 4);  // K-major 128-row tiles
     p.off_u_lo = o; if (p.tc) o = align_up(o + rows_tiled * p.IP * 4);
     p.off_gi = o;   o = align_up(o + rows * p.GP * 4);
-    p.off_z = o;    if (sparse) o = align_up(o + rows * (size_t)S * Fo * 4);
+    // sparse path scratch: row-major U (rows x S*Fo) + one [Fo][S] row per resident CTA
+    p.off_z = o;    if (sparse) o = align_up(o + (rows + wg::kNumSMs) * (size_t)S * Fo * 4);
     p.total = o;
     return WG_OK;
 }
@@ -268,10 +269,16 @@ int launch_gcn_sparse(const Plan& p, void* ws, const Csr& g, const float* x, con
         auto kern = (p.Fi <= 13 && p.Fo <= 13) ? wg::gcn_sparse_row_kernel<13> : wg::gcn_sparse_row_kernel<16>;
         WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
         const unsigned grid = (unsigned)(rows < wg::kNumSMs ? rows : wg::kNumSMs);
-        // off_z holds rows * S * F_out floats: its first gridDim rows serve as the per-CTA scratch rows
-        kern<<<grid, wg::kSrThreads, smem_row, st>>>(
-            x, g.rowptr, g.colidx, g.vals, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_z), ws_ptr<float>(ws, p.off_u), rows,
-            p.S, p.Fi, p.Fh, p.Fo, p.IP);
+        // off_z: [rows][S*Fo] row-major U, then gridDim per-CTA Z rows
+        float* urow = ws_ptr<float>(ws, p.off_z);
+        float* zscr = urow + (size_t)rows * p.S * p.Fo;
+        kern<<<grid, wg::kSrThreads, smem_row, st>>>(x, g.rowptr, g.colidx, g.vals, w1, b1, w2, b2, zscr, urow, rows,
+                                                     p.S, p.Fi, p.Fh, p.Fo);
+        WG_CUDA(cudaGetLastError());
+        const long long rt = (rows + wg::kSpThreads - 1) / wg::kSpThreads * wg::kSpThreads;  // whole tiles (zero rows)
+        const dim3 tg((unsigned)((p.IP + 31) / 32), (unsigned)(rt / 32));
+        if (tg.y > 65535u) return fail(WG_ERR_UNSUPPORTED, "sparse GCN: chunk of %lld rows too large", rows);
+        wg::rows_to_tiles_kernel<<<tg, 256, 0, st>>>(urow, ws_ptr<float>(ws, p.off_u), rows, p.S * p.Fo, p.IP);
         WG_CUDA(cudaGetLastError());
         return WG_OK;
     }

@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(kSpThreads)
 //           operand: h2[(s, s')] += w1[f][fh] * (agg_s[f], agg_s'[f]);  z2[f][(s, s')] += w2[fh][f] * h2.
 //           Z goes to a per-CTA scratch row in HBM/L2 as [F_out][S] (coalesced), is bulk-copied
 //           back over the slab once every thread is done with X;
-//   pass 2: U[s] = relu((A.Z)[s] + b2) written into the projection GEMM's K-major tiles.
+//   pass 2: U[s] = relu((A.Z)[s] + b2), written row-major (coalesced); rows_to_tiles_kernel then re-lays
+//           it into the projection GEMM's K-major 128-row tiles (a 4-byte scatter from here would
+//           double the DRAM write traffic through partial sectors).
 // The lane = row kernels above gather from HBM with one sector per lane; at S = 4096 this
 // variant is what runs (8x fewer bytes through L2, FMA-bound instead of latency-bound).
 constexpr int kSrThreads = 256;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kSrThreads, 1)
                           const int* __restrict__ colidx, const float* __restrict__ vals,
                           const float* __restrict__ W1, const float* __restrict__ b1,
                           const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ Zscr,
-                          float* __restrict__ U, long long R, int S, int Fi, int Fh, int Fo, int ldo) {
+                          float* __restrict__ U, long long R, int S, int Fi, int Fh, int Fo) {
     extern __shared__ __align__(16) float smem[];
     const int FS = Fi > Fo ? Fi : Fo;
     float* slab = smem;                                    // X row [S][Fi], then Z row [Fo][S]
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kSrThreads, 1)
                 en[i] = s < S ? __ldg(rowptr + s + 1) - eb[i] : 0;
                 nmax = en[i] > nmax ? en[i] : nmax;
             }
+#pragma unroll 2
             for (int j = 0; j < nmax; ++j) {
                 float a[kSrGroup];
                 const float* xs[kSrGroup];
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(kSrThreads, 1)
             __syncthreads();
         }
         // ---- pass 2: U[s] = relu((A.Z)[s] + b2), tiled store ----
-        float* ut = U + (size_t)(r / kSpThreads) * ldo * kSpThreads + (r % kSpThreads);
+        float* urow = U + (size_t)r * S * Fo;   // row-major [R][S * Fo]; rows_to_tiles_kernel re-lays it
         for (int base = 0; base < S; base += kSrThreads * kSrGroup) {
             float acc[kSrGroup][FW];
             int eb[kSrGroup], en[kSrGroup], nmax = 0;
@@ -309,6 +312,7 @@ __global__ void __launch_bounds__(kSrThreads, 1)
 #pragma unroll
                 for (int f = 0; f < FW; ++f) acc[i][f] = 0.0f;
             }
+#pragma unroll 2
             for (int j = 0; j < nmax; ++j) {
                 float a[kSrGroup];
                 const float* zs[kSrGroup];
@@ -333,14 +337,36 @@ __global__ void __launch_bounds__(kSrThreads, 1)
                         if (f < Fo) {
                             float v = acc[i][f] + b2s[f];
                             v = v < 0.0f ? 0.0f : v;
-                            ut[(size_t)(s * Fo + f) * kSpThreads] = v;
+                            urow[(size_t)s * Fo + f] = v;
                         }
                     }
                 }
             }
         }
-        for (int c = S * Fo + tid; c < ldo; c += kSrThreads) ut[(size_t)c * kSpThreads] = 0.0f;  // K padding
         __syncthreads();   // the slab is free for the next row's bulk copy
+    }
+}
+
+// Urow [R][K] row-major -> U tiles [ceil(R/128)][ldo][128] (K-major), columns K .. ldo zeroed, rows
+// beyond R zeroed.  32 x 32 shared-memory transpose; grid = (ceil(ldo / 32), ceil(R / 32)).
+__global__ void __launch_bounds__(256) rows_to_tiles_kernel(const float* __restrict__ Urow, float* __restrict__ U,
+                                                            long long R, int K, int ldo) {
+    __shared__ float t[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const long long r0 = (long long)blockIdx.y * 32;
+    const int k0 = blockIdx.x * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = r0 + ty + 8 * i;
+        const int k = k0 + tx;
+        t[ty + 8 * i][tx] = (r < R && k < K) ? __ldg(Urow + (size_t)r * K + k) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = k0 + ty + 8 * i;
+        const long long r = r0 + tx;
+        if (k < ldo) U[(size_t)(r / kSpThreads) * ldo * kSpThreads + (size_t)k * kSpThreads + (r % kSpThreads)] = t[tx][ty + 8 * i];
     }
 }
 
