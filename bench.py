@@ -505,7 +505,7 @@ def main():
         xh = torch.empty((Bg, T, S, F), dtype=torch.float32, pin_memory=True)
         xh.copy_(x)
         oh = torch.empty((Bg, T, H), dtype=torch.float32, pin_memory=True)
-        model.chunk = 512  # pipeline granularity: H2D / compute / D2H of consecutive chunks overlap
+        model.chunk = 256  # pipeline granularity: H2D / compute (two lanes) / D2H of consecutive chunks overlap
         e2e_steps = max(3, min(steps, 10))
         with torch.no_grad():
             for _ in range(2):
@@ -519,7 +519,7 @@ def main():
         model.chunk = 0
         e2e = {"value": world * Bg * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": Bg * T * S * F * 4, "d2h_bytes_per_step": Bg * T * H * 4,
-               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "pipeline_chunk": 512}
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "pipeline_chunk": 256, "compute_lanes": 2}
         del xh, oh
     barrier()
 

@@ -688,14 +688,19 @@ int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, con
 }
 
 // ---- host-buffer variant: H2D / compute / D2H of consecutive chunks overlapped ----------------
-// workspace = [ compute workspace | x staging 0 | x staging 1 | out staging 0 | out staging 1 ]
+// Two compute lanes (streams, each with its own scratch) so that the latency-bound recurrence of chunk c
+// overlaps the GCN / projection of chunk c+1; three staging slots each for x and out.
+// workspace = [ compute workspace 0 | compute workspace 1 | x staging 0..2 | out staging 0..2 ]
+constexpr int kHostLanes = 2;
+constexpr int kHostSlots = 3;
+
 size_t wg_gcn_gru_host_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
                                        int64_t chunk, int flags) {
     Plan p;
     if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, false, flags)) return 0;
     const size_t xs = align_up((size_t)p.chunk * T * S * F_in * 4);
     const size_t os = align_up((size_t)p.chunk * T * H * 4);
-    return p.total + 2 * xs + 2 * os;
+    return kHostLanes * align_up(p.total) + kHostSlots * (xs + os);
 }
 
 int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const float* w1, const float* b1,
@@ -711,31 +716,38 @@ int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const flo
         return fail(WG_ERR_BAD_ARG, "null pointer argument");
     const size_t xs = align_up((size_t)p.chunk * T * S * F_in * 4);
     const size_t os = align_up((size_t)p.chunk * T * H * 4);
+    const size_t wsz = align_up(p.total);
+    const size_t need = kHostLanes * wsz + kHostSlots * (xs + os);
     if (!workspace || reinterpret_cast<uintptr_t>(workspace) % kAlign)
         return fail(WG_ERR_WORKSPACE, "workspace NULL or not %zu-byte aligned", kAlign);
-    if (workspace_bytes < p.total + 2 * xs + 2 * os)
-        return fail(WG_ERR_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", workspace_bytes,
-                    p.total + 2 * xs + 2 * os);
+    if (workspace_bytes < need)
+        return fail(WG_ERR_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
     DeviceGuard g(device);
     WG_CUDA(g.err);
 
     char* base = static_cast<char*>(workspace);
-    float* xdev[2] = {reinterpret_cast<float*>(base + p.total), reinterpret_cast<float*>(base + p.total + xs)};
-    float* odev[2] = {reinterpret_cast<float*>(base + p.total + 2 * xs),
-                      reinterpret_cast<float*>(base + p.total + 2 * xs + os)};
+    void* lane_ws[kHostLanes];
+    for (int l = 0; l < kHostLanes; ++l) lane_ws[l] = base + l * wsz;
+    float* xdev[kHostSlots];
+    float* odev[kHostSlots];
+    for (int i = 0; i < kHostSlots; ++i) {
+        xdev[i] = reinterpret_cast<float*>(base + kHostLanes * wsz + i * xs);
+        odev[i] = reinterpret_cast<float*>(base + kHostLanes * wsz + kHostSlots * xs + i * os);
+    }
 
-    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[kHostLanes] = {};
+    cudaEvent_t ev_in[kHostSlots] = {}, ev_cmp[kHostSlots] = {}, ev_out[kHostSlots] = {};
     int result = WG_OK;
     auto cleanup = [&]() {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kHostSlots; ++i) {
             if (ev_in[i]) cudaEventDestroy(ev_in[i]);
             if (ev_cmp[i]) cudaEventDestroy(ev_cmp[i]);
             if (ev_out[i]) cudaEventDestroy(ev_out[i]);
         }
         if (s_in) cudaStreamDestroy(s_in);
-        if (s_cmp) cudaStreamDestroy(s_cmp);
         if (s_out) cudaStreamDestroy(s_out);
+        for (int l = 0; l < kHostLanes; ++l)
+            if (s_cmp[l]) cudaStreamDestroy(s_cmp[l]);
     };
 #define WG_CUDA_H(expr)                                                                         \
     do {                                                                                        \
@@ -750,45 +762,48 @@ int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const flo
     } while (0)
 
     WG_CUDA_H(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    WG_CUDA_H(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
     WG_CUDA_H(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int l = 0; l < kHostLanes; ++l) WG_CUDA_H(cudaStreamCreateWithFlags(&s_cmp[l], cudaStreamNonBlocking));
+    for (int i = 0; i < kHostSlots; ++i) {
         WG_CUDA_H(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
         WG_CUDA_H(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming));
         WG_CUDA_H(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
     }
-    if ((rc = launch_pack(p, workspace, w_ih, w_hh, b_ih, b_hh, s_cmp))) {
-        cudaDeviceSynchronize();
-        cleanup();
-        return rc;
-    }
-    const size_t x_seq = (size_t)T * S * F_in, o_seq = (size_t)T * H;
-    long long n_chunks = (B + p.chunk - 1) / p.chunk;
-    for (long long c = 0; c < n_chunks; ++c) {
-        const int sl = (int)(c & 1);
-        const long long b0 = c * p.chunk;
-        const long long Bc = (B - b0) < p.chunk ? (B - b0) : p.chunk;
-        // x staging slot is free once the compute that read it (chunk c-2) is done
-        if (c >= 2) WG_CUDA_H(cudaStreamWaitEvent(s_in, ev_cmp[sl], 0));
-        WG_CUDA_H(cudaMemcpyAsync(xdev[sl], x_host + (size_t)b0 * x_seq, (size_t)Bc * x_seq * 4,
-                                  cudaMemcpyHostToDevice, s_in));
-        WG_CUDA_H(cudaEventRecord(ev_in[sl], s_in));
-        // compute waits for its input and for the D2H that last used this out slot (chunk c-2)
-        WG_CUDA_H(cudaStreamWaitEvent(s_cmp, ev_in[sl], 0));
-        if (c >= 2) WG_CUDA_H(cudaStreamWaitEvent(s_cmp, ev_out[sl], 0));
-        if ((rc = run_chunk(p, workspace, adj, xdev[sl], w1, b1, w2, b2, odev[sl], Bc, s_cmp))) {
+    const long long n_chunks = (B + p.chunk - 1) / p.chunk;
+    for (int l = 0; l < kHostLanes && l < n_chunks; ++l) {   // each lane packs the parameters into its own scratch
+        if ((rc = launch_pack(p, lane_ws[l], w_ih, w_hh, b_ih, b_hh, s_cmp[l]))) {
             cudaDeviceSynchronize();
             cleanup();
             return rc;
         }
-        WG_CUDA_H(cudaEventRecord(ev_cmp[sl], s_cmp));
+    }
+    const size_t x_seq = (size_t)T * S * F_in, o_seq = (size_t)T * H;
+    for (long long c = 0; c < n_chunks; ++c) {
+        const int sl = (int)(c % kHostSlots), lane = (int)(c % kHostLanes);
+        const long long b0 = c * p.chunk;
+        const long long Bc = (B - b0) < p.chunk ? (B - b0) : p.chunk;
+        // x staging slot is free once the compute that read it (chunk c - slots) is done
+        if (c >= kHostSlots) WG_CUDA_H(cudaStreamWaitEvent(s_in, ev_cmp[sl], 0));
+        WG_CUDA_H(cudaMemcpyAsync(xdev[sl], x_host + (size_t)b0 * x_seq, (size_t)Bc * x_seq * 4,
+                                  cudaMemcpyHostToDevice, s_in));
+        WG_CUDA_H(cudaEventRecord(ev_in[sl], s_in));
+        // compute waits for its input and for the D2H that last used this out slot (chunk c - slots);
+        // the lane's scratch is free because chunk c - lanes ran on the same stream
+        WG_CUDA_H(cudaStreamWaitEvent(s_cmp[lane], ev_in[sl], 0));
+        if (c >= kHostSlots) WG_CUDA_H(cudaStreamWaitEvent(s_cmp[lane], ev_out[sl], 0));
+        if ((rc = run_chunk(p, lane_ws[lane], adj, xdev[sl], w1, b1, w2, b2, odev[sl], Bc, s_cmp[lane]))) {
+            cudaDeviceSynchronize();
+            cleanup();
+            return rc;
+        }
+        WG_CUDA_H(cudaEventRecord(ev_cmp[sl], s_cmp[lane]));
         WG_CUDA_H(cudaStreamWaitEvent(s_out, ev_cmp[sl], 0));
         WG_CUDA_H(cudaMemcpyAsync(out_host + (size_t)b0 * o_seq, odev[sl], (size_t)Bc * o_seq * 4,
                                   cudaMemcpyDeviceToHost, s_out));
         WG_CUDA_H(cudaEventRecord(ev_out[sl], s_out));
     }
     WG_CUDA_H(cudaStreamSynchronize(s_out));
-    WG_CUDA_H(cudaStreamSynchronize(s_cmp));
+    for (int l = 0; l < kHostLanes; ++l) WG_CUDA_H(cudaStreamSynchronize(s_cmp[l]));
     WG_CUDA_H(cudaStreamSynchronize(s_in));
 #undef WG_CUDA_H
     cleanup();
