@@ -25,7 +25,9 @@
 
 namespace wg {
 
-constexpr int kGbwFS = 16;  // floats per station in the padded slabs
+constexpr int kGbwW = 16;   // width of the zero-padded weight tables
+constexpr int kGbwFS = 20;  // floats per station in the padded slabs: 16 used + 4 so that the stations a warp's
+                            // lanes own (consecutive stations, 80 B apart) fall into distinct bank groups
 constexpr int kGbwThreads = 256;
 // padded slab row stride: + 4 floats so that the rows a warp touches at once start in different banks
 __host__ __device__ inline int gcn_bwd_row_stride(int S) { return S * kGbwFS + 4; }
@@ -35,8 +37,8 @@ __host__ __device__ inline size_t gcn_bwd_smem_floats(int S, int Fo, int RB) {
     const int NSG = ceil_div(S, SG);
     size_t n = 0;
     n += 2 * (size_t)S * NSG * 8;          // adjT (A[own][sp]) and adjN (A[sp][own])
-    n += 3 * (size_t)kGbwFS * kGbwFS;      // W1, W2, W2^T (zero padded 16 x 16)
-    n += 2 * (size_t)kGbwFS;               // b1, b2
+    n += 3 * (size_t)kGbwW * kGbwW;        // W1, W2, W2^T (zero padded 16 x 16)
+    n += 2 * (size_t)kGbwW;                // b1, b2
     n += 3 * (size_t)RB * gcn_bwd_row_stride(S);  // padded slabs s0, s1, s2
     n += (size_t)round_up(RB * S * Fo, 4); // dense dU block
     n += 4;                                // mbarrier
@@ -95,7 +97,7 @@ __device__ __forceinline__ void gcn_bwd_xform4(float2 (&o)[SG][2], const float2 
     for (int i = 0; i < SG; ++i) o[i][0] = o[i][1] = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int f = 0; f < 2 * FPP; ++f) {
-        const float4 w = *reinterpret_cast<const float4*>(Wn + f * kGbwFS + fo0);
+        const float4 w = *reinterpret_cast<const float4*>(Wn + f * kGbwW + fo0);
 #pragma unroll
         for (int i = 0; i < SG; ++i) {
             const float av = (f & 1) ? in[i][f >> 1].y : in[i][f >> 1].x;
@@ -117,38 +119,39 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
     extern __shared__ __align__(16) float smem[];
     const int NSG = ceil_div(S, SG);
     const int tid = threadIdx.x;
-    const int astride = NSG * 8;
+    constexpr int TS = SG > 4 ? 8 : 4;   // table floats per station group (LDS.128 granules)
+    const int astride = NSG * TS;
     const int SR = gcn_bwd_row_stride(S);   // padded slab row stride
 
     float* adjT = smem;
     float* adjN = adjT + (size_t)S * NSG * 8;
     float* w1d = adjN + (size_t)S * NSG * 8;
-    float* w2d = w1d + kGbwFS * kGbwFS;
-    float* w2t = w2d + kGbwFS * kGbwFS;
-    float* b1s = w2t + kGbwFS * kGbwFS;
-    float* b2s = b1s + kGbwFS;
-    float* s0 = b2s + kGbwFS;                  // X (dense, on arrival) -> AX (padded)
+    float* w2d = w1d + kGbwW * kGbwW;
+    float* w2t = w2d + kGbwW * kGbwW;
+    float* b1s = w2t + kGbwW * kGbwW;
+    float* b2s = b1s + kGbwW;
+    float* s0 = b2s + kGbwW;                  // X (dense, on arrival) -> AX (padded)
     float* s1 = s0 + (size_t)RB * SR;          // G1 -> AG -> dZ1
     float* s2 = s1 + (size_t)RB * SR;          // dZ2 -> dAG
     float* sd = s2 + (size_t)RB * SR;          // dU (dense)
     uint64_t* bar = reinterpret_cast<uint64_t*>(sd + round_up(RB * S * Fo, 4));
 
-    for (int e = tid; e < S * NSG * 8; e += kGbwThreads) {
-        const int sp = e / (NSG * 8);
-        const int c = e % (NSG * 8);
-        const int qq = c >> 3, i = c & 7;
-        const int s = qq * SG + i;
+    for (int e = tid; e < S * NSG * TS; e += kGbwThreads) {
+        const int sp = e / (NSG * TS);
+        const int c = e % (NSG * TS);
+        const int qq = c / TS, i = c % TS;
+        const int s = qq + NSG * i;       // thread qq owns stations qq, qq + NSG, ... (lanes = consecutive stations)
         const bool ok = i < SG && s < S;
         adjT[e] = ok ? adj[(size_t)s * S + sp] : 0.0f;
         adjN[e] = ok ? adj[(size_t)sp * S + s] : 0.0f;
     }
-    for (int e = tid; e < kGbwFS * kGbwFS; e += kGbwThreads) {
-        const int f = e / kGbwFS, fo = e % kGbwFS;
+    for (int e = tid; e < kGbwW * kGbwW; e += kGbwThreads) {
+        const int f = e / kGbwW, fo = e % kGbwW;
         w1d[e] = (f < Fi && fo < Fh) ? W1[f * Fh + fo] : 0.0f;
         w2d[e] = (f < Fh && fo < Fo) ? W2[f * Fo + fo] : 0.0f;
         w2t[e] = (f < Fo && fo < Fh) ? W2[fo * Fo + f] : 0.0f;   // w2t[fo'][f'] = W2[f'][fo']
     }
-    for (int e = tid; e < kGbwFS; e += kGbwThreads) {
+    for (int e = tid; e < kGbwW; e += kGbwThreads) {
         b1s[e] = e < Fh ? b1[e] : 0.0f;
         b2s[e] = e < Fo ? b2[e] : 0.0f;
     }
@@ -222,13 +225,13 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
 
         // ---- P1: AX = A.X (own stations) ; G1 = relu(AX.W1 + b1) ----
         if (active)
-            gcn_bwd_agg<FPP, SG, false>(acc, s0 + (size_t)row_local * in_cols, Fi, Fi, adjT + q * 8, astride, S);
+            gcn_bwd_agg<FPP, SG, false>(acc, s0 + (size_t)row_local * in_cols, Fi, Fi, adjT + q * TS, astride, S);
         __syncthreads();   // every read of the dense X block is done: s0 becomes the padded AX slab
         if (active) {
 #pragma unroll
             for (int i = 0; i < SG; ++i) {
                 mask1[i] = 0u;
-                const int s = q * SG + i;
+                const int s = q + NSG * i;
                 if (s < S) {
                     float* ax = s0 + (size_t)row_local * SR + s * kGbwFS;
 #pragma unroll
@@ -237,13 +240,13 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
                 }
             }
 #pragma unroll 1
-            for (int fo0 = 0; fo0 < kGbwFS; fo0 += 4) {
+            for (int fo0 = 0; fo0 < kGbwW; fo0 += 4) {
                 float2 o[SG][2];
                 gcn_bwd_xform4<FPP, SG>(o, acc, w1d, fo0);
                 const float4 bb = *reinterpret_cast<const float4*>(b1s + fo0);
 #pragma unroll
                 for (int i = 0; i < SG; ++i) {
-                    const int s = q * SG + i;
+                    const int s = q + NSG * i;
                     if (s < S) {
                         float4 g;
                         g.x = o[i][0].x + bb.x; g.y = o[i][0].y + bb.y; g.z = o[i][1].x + bb.z; g.w = o[i][1].y + bb.w;
@@ -260,12 +263,12 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
 
         // ---- P2: AG = A.G1 ; dZ2 = dU * [AG.W2 + b2 > 0] ----
         if (active)
-            gcn_bwd_agg<FPP, SG, true>(acc, s1 + (size_t)row_local * SR, kGbwFS, 2 * FPP, adjT + q * 8, astride, S);
+            gcn_bwd_agg<FPP, SG, true>(acc, s1 + (size_t)row_local * SR, kGbwFS, 2 * FPP, adjT + q * TS, astride, S);
         __syncthreads();   // every read of G1 is done: s1 becomes AG
         if (active) {
 #pragma unroll
             for (int i = 0; i < SG; ++i) {
-                const int s = q * SG + i;
+                const int s = q + NSG * i;
                 if (s < S) {
                     float* ag = s1 + (size_t)row_local * SR + s * kGbwFS;
 #pragma unroll
@@ -274,13 +277,13 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
                 }
             }
 #pragma unroll 1
-            for (int fo0 = 0; fo0 < kGbwFS; fo0 += 4) {
+            for (int fo0 = 0; fo0 < kGbwW; fo0 += 4) {
                 float2 o[SG][2];
                 gcn_bwd_xform4<FPP, SG>(o, acc, w2d, fo0);
                 const float4 bb = *reinterpret_cast<const float4*>(b2s + fo0);
 #pragma unroll
                 for (int i = 0; i < SG; ++i) {
-                    const int s = q * SG + i;
+                    const int s = q + NSG * i;
                     if (s < S) {
                         const float* du = sd + (size_t)row_local * du_cols + s * Fo + fo0;
                         float4 d;
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
         if (active) {   // own dZ2 rows into registers (reads only) before anyone overwrites s2
 #pragma unroll
             for (int i = 0; i < SG; ++i) {
-                const int s = q * SG + i;
+                const int s = q + NSG * i;
                 const float* dz = s2 + (size_t)row_local * SR + (s < S ? s : 0) * kGbwFS;
 #pragma unroll
                 for (int fp = 0; fp < FPP; ++fp) acc[i][fp] = *reinterpret_cast<const float2*>(dz + 2 * fp);
@@ -309,12 +312,12 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
         __syncthreads();   // the reduction has read every dZ2
         if (active) {
 #pragma unroll 1
-            for (int fo0 = 0; fo0 < kGbwFS; fo0 += 4) {
+            for (int fo0 = 0; fo0 < kGbwW; fo0 += 4) {
                 float2 o[SG][2];
                 gcn_bwd_xform4<FPP, SG>(o, acc, w2t, fo0);
 #pragma unroll
                 for (int i = 0; i < SG; ++i) {
-                    const int s = q * SG + i;
+                    const int s = q + NSG * i;
                     if (s < S)
                         *reinterpret_cast<float4*>(s2 + (size_t)row_local * SR + s * kGbwFS + fo0) =
                             make_float4(o[i][0].x, o[i][0].y, o[i][1].x, o[i][1].y);
@@ -325,10 +328,10 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
 
         // ---- P4: dG1 = A^T dAG ; dZ1 = dG1 * [G1 > 0] -> s1 ----
         if (active) {
-            gcn_bwd_agg<FPP, SG, true>(acc, s2 + (size_t)row_local * SR, kGbwFS, 2 * FPP, adjN + q * 8, astride, S);
+            gcn_bwd_agg<FPP, SG, true>(acc, s2 + (size_t)row_local * SR, kGbwFS, 2 * FPP, adjN + q * TS, astride, S);
 #pragma unroll
             for (int i = 0; i < SG; ++i) {
-                const int s = q * SG + i;
+                const int s = q + NSG * i;
                 if (s < S) {
                     float* dz = s1 + (size_t)row_local * SR + s * kGbwFS;
 #pragma unroll
