@@ -78,12 +78,13 @@ def test_flat_backward_matches_oracle_with_arbitrary_upstream_gradient(S):
 
 
 def test_gradients_ragged_batches_and_short_windows():
-    """Batch sizes that do not fill a CTA (16 / 32 sequences), T = 1 and odd T."""
+    """Batch sizes that do not fill a CTA (4 / 16 / 32 sequences), T = 1 and odd T; 601 windows is past the
+    switch from 4 to 16 sequences per CTA in the BPTT kernel."""
     sd = load_checkpoint(7)
     model = _model(7, sd)
     adj = _adj(7)
     rng = np.random.default_rng(11)
-    for B, T in ((1, 1), (5, 3), (17, 6), (37, 9)):
+    for B, T in ((1, 1), (5, 3), (17, 6), (37, 9), (601, 4)):
         x = rng.random((B, T, 7, 13), dtype=np.float32)
         y = rng.random((B, T, 21), dtype=np.float32)
         with torch.no_grad():

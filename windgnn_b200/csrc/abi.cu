@@ -435,7 +435,7 @@ bool any_null(std::initializer_list<const void*> ps) {
 struct TrainPlan {
     Plan f;            // the forward's plan (chunk == B, FP32 path, dense graph)
     int LD4;           // row stride of the gate / DG buffers: 4H rounded up to 4
-    int HP, GR;        // gru_bwd: H rounded up to 4, 3H rounded up to 8
+    int HP, GR, bt_gb; // gru_bwd: H rounded up to 4, padded contraction length, sequences per CTA (16 or 4)
     long long rows;    // B * T
     int grid_gb;       // CTAs of the backward recurrence
     int grid_gcn, rb_gcn, sg_gcn, fp_gcn;
@@ -465,11 +465,15 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
         return fail(WG_ERR_UNSUPPORTED, "training: GCN feature widths must be <= 16 (got %d / %d / %d)", Fi, Fh, Fo);
     tp.LD4 = wg::round_up(4 * H, 4);
     tp.HP = wg::round_up(H, 4);
-    tp.GR = wg::round_up(3 * H, 8);
-    if (tp.HP > 128 || wg::gru_bwd_smem_floats(tp.HP, tp.GR) * 4 > (size_t)wg::kMaxSmemOptin)
+    // 16 sequences per CTA when that fills the machine, else 4 (the recurrence is latency-bound: with few
+    // sequences per GPU — configs[4]: 512 — more, lighter CTAs shorten every one of the T serial steps)
+    tp.bt_gb = (B > 0 ? B : 1) > 4LL * wg::kNumSMs ? wg::kGbBT : 4;
+    tp.GR = wg::gru_bwd_gr(H, tp.bt_gb);
+    if (tp.HP > 128 || (tp.HP / 4) * (tp.bt_gb / 4) * wg::gru_bwd_ksplit(tp.bt_gb) > wg::kGbThreads ||
+        wg::gru_bwd_smem_floats(tp.HP, tp.GR, tp.bt_gb) * 4 > (size_t)wg::kMaxSmemOptin)
         return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d too large for the shared-memory BPTT kernel", H);
     tp.rows = (B > 0 ? B : 1) * (long long)T;
-    tp.grid_gb = (int)(((B > 0 ? B : 1) + wg::kGbBT - 1) / wg::kGbBT);
+    tp.grid_gb = (int)(((B > 0 ? B : 1) + tp.bt_gb - 1) / tp.bt_gb);
     // GCN backward geometry (same station grouping as the forward)
     // 4 stations per thread: the slabs bound the CTA to ~24 rows, so the narrower station group is what
     // puts 7 warps instead of 4 on the SM
@@ -904,10 +908,10 @@ int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, c
 
     // 1. BPTT through the recurrence: DG = [da_r | da_z | da_n | da_n r], bias partials
     {
-        const size_t smem = wg::gru_bwd_smem_floats(tp.HP, tp.GR) * 4;
-        WG_CUDA(cudaFuncSetAttribute(wg::gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        wg::gru_bwd_kernel<<<tp.grid_gb, wg::kGbThreads, smem, st>>>(gates, out, d_out, w_hh, DG, biasp, B, T, H, tp.LD4,
-                                                                    tp.HP, tp.GR);
+        const size_t smem = wg::gru_bwd_smem_floats(tp.HP, tp.GR, tp.bt_gb) * 4;
+        auto kern = tp.bt_gb == 4 ? wg::gru_bwd_kernel<4> : wg::gru_bwd_kernel<wg::kGbBT>;
+        WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<tp.grid_gb, wg::kGbThreads, smem, st>>>(gates, out, d_out, w_hh, DG, biasp, B, T, H, tp.LD4, tp.HP, tp.GR);
         WG_CUDA(cudaGetLastError());
         wg::gru_bias_grad_kernel<<<(4 * H + 127) / 128, 128, 0, st>>>(biasp, tp.grid_gb * 2, H, tp.LD4, d_bih, d_bhh);
         WG_CUDA(cudaGetLastError());

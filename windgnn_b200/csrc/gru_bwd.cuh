@@ -23,8 +23,11 @@
 
 namespace wg {
 
-constexpr int kGbBT = 16;        // sequences per CTA
+constexpr int kGbBT = 16;        // sequences per CTA (large batches); 4 when the batch would not fill the SMs
 constexpr int kGbThreads = 256;
+// contraction splits: (BT / 4) row groups x 26 column groups x KS splits = 208 threads for H = 102
+__host__ __device__ constexpr int gru_bwd_ksplit(int BT) { return 32 / BT; }
+__host__ __device__ inline int gru_bwd_gr(int H, int BT) { return round_up(3 * H, 4 * gru_bwd_ksplit(BT)); }
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, bool pred) {
     const int src_bytes = pred ? 4 : 0;
@@ -39,17 +42,18 @@ __device__ __forceinline__ void cp_async8z(void* smem_dst, const void* gmem_src,
                  : "memory");
 }
 
-// HP = H rounded up to 4 (row stride of the per-sequence vectors), GR = 3H rounded up to 8
-// (contraction length, split in two halves of GR / 2, each a multiple of 4).
-__host__ __device__ inline size_t gru_bwd_smem_floats(int HP, int GR) {
+// HP = H rounded up to 4 (row stride of the per-sequence vectors), GR = 3H rounded up so that each of
+// the KS contraction splits is a multiple of 4 long.
+__host__ __device__ inline size_t gru_bwd_smem_floats(int HP, int GR, int BT = kGbBT) {
     size_t n = 0;
-    n += (size_t)GR * HP;           // W_hh rows (zero padded)
-    n += (size_t)kGbBT * (GR + 4);  // dgh of the current step
-    n += 3 * (size_t)kGbBT * HP;    // D (g z), P0, P1 (the two halves of dgh . W_hh)
-    n += 6 * (size_t)kGbBT * HP;    // staged inputs of one step: dout, r, z, n, hn, h_prev
+    n += (size_t)GR * HP;                              // W_hh rows (zero padded)
+    n += (size_t)BT * (GR + 4);                        // dgh of the current step
+    n += (size_t)(1 + gru_bwd_ksplit(BT)) * BT * HP;   // D (g z) and the KS partial products of dgh . W_hh
+    n += 6 * (size_t)BT * HP;                          // staged inputs of one step: dout, r, z, n, hn, h_prev
     return n;
 }
 
+template <int BT>
 __global__ void __launch_bounds__(kGbThreads, 1)
     gru_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ out, const float* __restrict__ dout,
                    const float* __restrict__ w_hh, float* __restrict__ DG, float* __restrict__ bias_part,
@@ -57,23 +61,23 @@ __global__ void __launch_bounds__(kGbThreads, 1)
     extern __shared__ __align__(16) float smem[];
     const int DS = GR + 4;  // dgh row stride: rows 4 apart land in different banks
     float* Ws = smem;                         // [GR][HP]
-    float* dgh = Ws + (size_t)GR * HP;        // [16][DS]
-    float* Dd = dgh + kGbBT * DS;             // [16][HP]
-    float* P0 = Dd + kGbBT * HP;
-    float* P1 = P0 + kGbBT * HP;
-    float* stg = P1 + kGbBT * HP;             // [6][16][HP]
+    constexpr int KS = gru_bwd_ksplit(BT);
+    float* dgh = Ws + (size_t)GR * HP;        // [BT][DS]
+    float* Dd = dgh + BT * DS;                // [BT][HP]
+    float* Pp = Dd + BT * HP;                 // [KS][BT][HP]
+    float* stg = Pp + KS * BT * HP;           // [6][BT][HP]
 
     const int tid = threadIdx.x;
-    const long long b0 = (long long)blockIdx.x * kGbBT;
+    const long long b0 = (long long)blockIdx.x * BT;
     const int G = 3 * H;
 
     for (int e = tid; e < GR * HP; e += kGbThreads) {
         const int n = e / HP, k = e - n * HP;
         Ws[e] = (n < G && k < H) ? __ldg(w_hh + (size_t)n * H + k) : 0.0f;
     }
-    for (int e = tid; e < kGbBT * DS; e += kGbThreads) dgh[e] = 0.0f;
-    for (int e = tid; e < 3 * kGbBT * HP; e += kGbThreads) Dd[e] = 0.0f;      // D, P0, P1
-    for (int e = tid; e < 6 * kGbBT * HP; e += kGbThreads) stg[e] = 0.0f;
+    for (int e = tid; e < BT * DS; e += kGbThreads) dgh[e] = 0.0f;
+    for (int e = tid; e < (1 + KS) * BT * HP; e += kGbThreads) Dd[e] = 0.0f;      // D and the partials
+    for (int e = tid; e < 6 * BT * HP; e += kGbThreads) stg[e] = 0.0f;
 
     // ---- staging of one step's inputs: six H-long rows per sequence ----
     const bool even = (H & 1) == 0 && (LD4 & 1) == 0 &&
@@ -82,8 +86,8 @@ __global__ void __launch_bounds__(kGbThreads, 1)
     // a warp takes (input, sequence) rows w, w + 8, ...; its lanes walk the row (no divisions)
     auto prefetch = [&](int t) {
         const int per_row = even ? (H >> 1) : H;       // copies per row
-        for (int rb = tid >> 5; rb < 6 * kGbBT; rb += kGbThreads / 32) {
-            const int b = rb % kGbBT, q = rb / kGbBT;
+        for (int rb = tid >> 5; rb < 6 * BT; rb += kGbThreads / 32) {
+            const int b = rb % BT, q = rb / BT;
             const bool ok = (b0 + b < B) && !(q == 5 && t == 0);
             const size_t row = (size_t)(b0 + b) * T + t;
             const float* src = dout;                         // any valid address when !ok (zero fill)
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(kGbThreads, 1)
                 else if (q == 5) src = out + (row - 1) * H;  // h_prev = out[b, t - 1]
                 else src = gates + row * LD4 + (size_t)(q - 1) * H;
             }
-            float* dst = stg + ((size_t)q * kGbBT + b) * HP;
+            float* dst = stg + ((size_t)q * BT + b) * HP;
             if (even) {
                 for (int c = tid & 31; c < per_row; c += 32) cp_async8z(dst + 2 * c, ok ? src + 2 * c : src, ok);
             } else {
@@ -107,14 +111,14 @@ __global__ void __launch_bounds__(kGbThreads, 1)
 
     // gate-phase coordinates: hidden unit j (+128 ...) x half of the sequences
     const int gj = tid & 127;
-    const int gh_ = tid >> 7;              // 0 / 1: sequences [0, 8) / [8, 16)
-    // GEMM coordinates: contraction half kh, row group rg (4 sequences), column group cg (4 units)
+    const int gh_ = tid >> 7;              // 0 / 1: first / second half of the CTA's sequences
+    // GEMM coordinates: contraction split kh, row group rg (4 sequences), column group cg (4 units)
     const int n_cg = HP >> 2;
-    const int per_half = 4 * n_cg;
-    const int kh = tid / per_half;         // >= 2: idle in the GEMM
+    const int per_half = (BT / 4) * n_cg;
+    const int kh = tid / per_half;         // >= KS: idle in the GEMM
     const int rem = tid - kh * per_half;
     const int rg = rem / n_cg, cg = rem - rg * n_cg;
-    const int KH = GR >> 1;
+    const int KH = GR / KS;
 
     // per-thread column sums of DG over this CTA's sequences and all steps (hidden units gj, gj+128, ...)
     constexpr int kMaxJ = 1;   // H <= 128 (the launcher enforces HP <= 128)
@@ -132,13 +136,15 @@ __global__ void __launch_bounds__(kGbThreads, 1)
             const int j = gj + u * 128;
             if (j < H) {
 #pragma unroll
-                for (int bl = 0; bl < kGbBT / 2; ++bl) {
-                    const int b = gh_ * (kGbBT / 2) + bl;
+                for (int bl = 0; bl < BT / 2; ++bl) {
+                    const int b = gh_ * (BT / 2) + bl;
                     const int o = b * HP + j;
-                    const float g = stg[o] + Dd[o] + P0[o] + P1[o];
-                    const float r = stg[1 * kGbBT * HP + o], z = stg[2 * kGbBT * HP + o];
-                    const float n = stg[3 * kGbBT * HP + o], hn = stg[4 * kGbBT * HP + o];
-                    const float hp = stg[5 * kGbBT * HP + o];
+                    float g = stg[o] + Dd[o];
+#pragma unroll
+                    for (int p = 0; p < KS; ++p) g += Pp[p * BT * HP + o];
+                    const float r = stg[1 * BT * HP + o], z = stg[2 * BT * HP + o];
+                    const float n = stg[3 * BT * HP + o], hn = stg[4 * BT * HP + o];
+                    const float hp = stg[5 * BT * HP + o];
                     const float dn = g * (1.0f - z);
                     const float dz = g * (hp - n);
                     const float da_n = dn * (1.0f - n * n);
@@ -165,8 +171,8 @@ __global__ void __launch_bounds__(kGbThreads, 1)
         if (t == 0) break;
         prefetch(t - 1);   // lands during the GEMM
 
-        // ================= P = dgh . W_hh (two contraction halves) =================
-        if (kh < 2) {
+        // ================= P = dgh . W_hh (KS contraction splits) =================
+        if (kh < KS) {
             float2 acc[4][2];
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.0f, 0.0f);
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(kGbThreads, 1)
                     }
                 }
             }
-            float* P = kh == 0 ? P0 : P1;
+            float* P = Pp + kh * BT * HP;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 *reinterpret_cast<float4*>(P + (rg * 4 + i) * HP + cg * 4) =
