@@ -368,8 +368,29 @@ int launch_recur_ws(const Plan& p, void* ws, float* out, long long Bc, cudaStrea
     return launch_recur_t<16, WS>(p, ws, out, Bc, st);
 }
 
+// few sequences (the reference's batch-1 calls, small shards): 4 per CTA, bit-identical results
+bool recur_small_applies(const Plan& p, long long Bc) {
+    // up to two waves of 4-sequence CTAs (~0.55 ms each at T = 168) beat one pass of the 32-sequence kernel (1.4 ms)
+    return Bc <= 2LL * wg::kRsBT * wg::kNumSMs && (p.NPR / 4) * (wg::kRsBT / 2) <= wg::kRsThreads &&
+           wg::recur_small_smem_floats(p.KP, p.NPR, p.GP) * 4 <= (size_t)wg::kMaxSmemOptin;
+}
+template <bool SAVE>
+int launch_recur_small(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
+    const size_t smem = wg::recur_small_smem_floats(p.KP, p.NPR, p.GP) * 4;
+    auto kern = wg::gru_recur_small_kernel<SAVE>;
+    WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (Bc + wg::kRsBT - 1) / wg::kRsBT;
+    if (grid < 1) return WG_OK;
+    kern<<<(unsigned)grid, wg::kRsThreads, smem, st>>>(ws_ptr<float>(ws, p.off_gi), ws_ptr<float>(ws, p.off_wht),
+                                                      ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, p.GP, p.KP,
+                                                      p.NPR, gsave, ldsave);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
 // training forward: the same recurrence, additionally saving [r | z | n | hn] per (sequence, step)
 int launch_recur_save(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
+    if (recur_small_applies(p, Bc)) return launch_recur_small<true>(p, ws, out, Bc, st, gsave, ldsave);
     const size_t smem_ws = wg::recur_smem_floats(p.KP, p.NPR, p.GP, true) * 4;
     if (smem_ws > (size_t)wg::kMaxSmemOptin)
         return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d does not fit the shared-memory recurrence", p.H);
@@ -381,6 +402,7 @@ int launch_recur_save(const Plan& p, void* ws, float* out, long long Bc, cudaStr
 }
 
 int launch_recur(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
+    if (recur_small_applies(p, Bc)) return launch_recur_small<false>(p, ws, out, Bc, st, nullptr, 0);
     const size_t smem_ws = wg::recur_smem_floats(p.KP, p.NPR, p.GP, true) * 4;
     if (smem_ws <= (size_t)wg::kMaxSmemOptin) return launch_recur_ws<true>(p, ws, out, Bc, st);
     const size_t smem_nows = wg::recur_smem_floats(p.KP, p.NPR, p.GP, false) * 4;
