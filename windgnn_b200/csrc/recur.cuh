@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     // GEMM coordinates: row pair rp (sequences 2 rp, 2 rp + 1), column quad cq
     const int n_cq = NP >> 2;
     const int rp = tid / n_cq, cq = tid - rp * n_cq;
-    const bool gemm_thread = rp < kRsBT / 2;
+    const bool gemm_thread = rp < kRsBT / 2 && b0 + 2 * rp < B;   // a row pair beyond the batch does no work
 
     for (int t = 0; t < T; ++t) {
         if (t + 1 < T) prefetch(t + 1);
