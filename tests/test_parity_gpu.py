@@ -163,6 +163,23 @@ def test_full_size_chunking_and_sharding_invariance(full34):
     assert torch.equal(torch.cat(shards), y)
 
 
+def test_small_batch_recurrence_is_bit_identical_to_the_throughput_kernel(full34):
+    """Up to 1,184 sequences the 4-sequence-per-CTA recurrence runs, above that the 32-sequence one
+    (csrc/recur.cuh): same summation order, same gate expressions -> the same bits, for a single
+    window (the reference's batch-1 call, main.py:102), ragged CTAs and the 7-station model."""
+    model, adj, x, y = full34
+    with torch.no_grad():
+        for lo, hi in ((0, 1), (5, 8), (100, 703), (2000, 3184), (2000, 3185)):
+            assert torch.equal(model(adj, x[lo:hi]).reshape(hi - lo, 168, 102), y[lo:hi]), (lo, hi)
+    m7 = _model(7)
+    adj7 = torch.from_numpy(_adj(7)).to(DEV)
+    x7 = torch.rand((1300, 24, 7, 13), device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    with torch.no_grad():
+        big = m7(adj7, x7)                                            # 1300 > 1184: throughput kernel
+        small = torch.cat([m7(adj7, x7[:650]), m7(adj7, x7[650:])])   # 650 each: small-batch kernel
+    assert torch.equal(big, small)
+
+
 def test_full_size_determinism_and_permutation(full34):
     model, adj, x, y = full34
     perm = torch.randperm(512, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
