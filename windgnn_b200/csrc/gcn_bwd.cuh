@@ -33,14 +33,14 @@ constexpr int kGbwThreads = 256;
 __host__ __device__ inline int gcn_bwd_row_stride(int S) { return S * kGbwFS + 4; }
 
 template <int SG>
-__host__ __device__ inline size_t gcn_bwd_smem_floats(int S, int Fo, int RB) {
+__host__ __device__ inline size_t gcn_bwd_smem_floats(int S, int ldu, int RB) {
     const int NSG = ceil_div(S, SG);
     size_t n = 0;
     n += 2 * (size_t)S * NSG * 8;          // adjT (A[own][sp]) and adjN (A[sp][own])
     n += 3 * (size_t)kGbwW * kGbwW;        // W1, W2, W2^T (zero padded 16 x 16)
     n += 2 * (size_t)kGbwW;                // b1, b2
     n += 3 * (size_t)RB * gcn_bwd_row_stride(S);  // padded slabs s0, s1, s2
-    n += (size_t)round_up(RB * S * Fo, 4); // dense dU block
+    n += (size_t)round_up(RB * ldu, 4);    // dU block (row stride ldu >= S * F_out)
     n += 4;                                // mbarrier
     return n;
 }
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
     gcn_bwd_kernel(const float* __restrict__ X, const float* __restrict__ dU, const float* __restrict__ adj,
                    const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                    const float* __restrict__ b2, float* __restrict__ part, long long R, int S, int Fi, int Fh,
-                   int Fo, int RB) {
+                   int Fo, int RB, int ldu) {
     constexpr int FPP = (FP + 1) / 2;
     extern __shared__ __align__(16) float smem[];
     const int NSG = ceil_div(S, SG);
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
     float* s1 = s0 + (size_t)RB * SR;          // G1 -> AG -> dZ1
     float* s2 = s1 + (size_t)RB * SR;          // dZ2 -> dAG
     float* sd = s2 + (size_t)RB * SR;          // dU (dense)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sd + round_up(RB * S * Fo, 4));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sd + round_up(RB * ldu, 4));
 
     for (int e = tid; e < S * NSG * TS; e += kGbwThreads) {
         const int sp = e / (NSG * TS);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
     const int row_local = tid / NSG;
     const int q = tid % NSG;
     const long long nblocks = (R + RB - 1) / RB;
-    const int in_cols = S * Fi, du_cols = S * Fo;
+    const int in_cols = S * Fi, du_cols = ldu;   // dU rows are ldu floats apart (the GEMM that wrote them pads to 4)
     unsigned phase = 0;
 
     // reduction-phase coordinates: output tile (fi, fj) of 4 x 4, slice ks of the (row, station) index

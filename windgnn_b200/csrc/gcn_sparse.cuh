@@ -347,10 +347,10 @@ __global__ void __launch_bounds__(kSrThreads, 1)
     }
 }
 
-// Urow [R][K] row-major -> U tiles [ceil(R/128)][ldo][128] (K-major), columns K .. ldo zeroed, rows
-// beyond R zeroed.  32 x 32 shared-memory transpose; grid = (ceil(ldo / 32), ceil(R / 32)).
+// Urow [R][lds] row-major (first K columns used) -> U tiles [ceil(R/128)][ldo][128] (K-major), columns
+// K .. ldo zeroed, rows beyond R zeroed.  32 x 32 shared-memory transpose; grid = (ceil(ldo / 32), ceil(R / 32)).
 __global__ void __launch_bounds__(256) rows_to_tiles_kernel(const float* __restrict__ Urow, float* __restrict__ U,
-                                                            long long R, int K, int ldo) {
+                                                            long long R, int K, int lds, int ldo) {
     __shared__ float t[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     const long long r0 = (long long)blockIdx.y * 32;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) rows_to_tiles_kernel(const float* __restr
     for (int i = 0; i < 4; ++i) {
         const long long r = r0 + ty + 8 * i;
         const int k = k0 + tx;
-        t[ty + 8 * i][tx] = (r < R && k < K) ? __ldg(Urow + (size_t)r * K + k) : 0.0f;
+        t[ty + 8 * i][tx] = (r < R && k < K) ? __ldg(Urow + (size_t)r * lds + k) : 0.0f;
     }
     __syncthreads();
 #pragma unroll
