@@ -199,3 +199,32 @@ def test_training_rejects_what_it_does_not_support():
     assert lib.wg_gcn_gru_train_workspace_bytes(4, 8, 7, 13, 32, 13, 21) == 0      # hidden GCN width > 16
     assert "feature widths" in _lib.last_error()
     assert lib.wg_gcn_gru_train_workspace_bytes(4, 8, 300, 13, 13, 13, 900) == 0   # H too large for the BPTT kernel
+    assert lib.wg_gcn_gru_train_workspace_bytes(4, 8, 40, 13, 13, 13, 120) == 0    # W_hh no longer fits shared memory
+    assert "recurrence" in _lib.last_error()
+
+
+@pytest.mark.parametrize("S,H,B,T", [(1, 3, 5, 4), (3, 9, 33, 7), (12, 36, 70, 11), (20, 50, 31, 6), (35, 105, 9, 5),
+                                     (9, 27, 700, 3)])
+def test_gradients_ragged_model_shapes(S, H, B, T):
+    """Random models with odd station counts / hidden sizes (H odd, even-not-multiple-of-4, near the
+    shared-memory limit of the recurrence), batches that end inside a CTA and inside a GEMM tile, and a batch past the 16-sequence BPTT
+    switch: every GEMM edge predicate, unaligned leading dimension and padded column is exercised."""
+    torch.manual_seed(S * 100 + B)
+    m = windgnn_b200.GCN_GRU(13, 13, 13, 13 * S, H)
+    with torch.no_grad():
+        m.conv1.weight.mul_(0.3)
+        m.conv2.weight.mul_(0.3)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    rng = np.random.default_rng(B)
+    adj = (rng.random((S, S), dtype=np.float32) / S).astype(np.float32)
+    x = rng.random((B, T, S, 13), dtype=np.float32)
+    y = rng.random((B, T, H), dtype=np.float32)
+    m = m.to(DEV)
+    out = m(torch.from_numpy(adj).to(DEV), torch.from_numpy(x).to(DEV))
+    loss = torch.nn.MSELoss()(out.reshape(B, T, H), torch.from_numpy(y).to(DEV))
+    loss.backward()
+    ref_loss, _, G = gcn_gru_loss_and_grads(adj, x, y, sd, dtype=np.float64)
+    assert abs(loss.item() - ref_loss) <= 2e-6 * ref_loss
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        assert normalised_max_error(p.grad.cpu().numpy(), G[k]) <= TOL, k

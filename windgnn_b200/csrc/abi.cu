@@ -510,6 +510,8 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
     if (tp.HP > 128 || (tp.HP / 4) * (tp.bt_gb / 4) * wg::gru_bwd_ksplit(tp.bt_gb) > wg::kGbThreads ||
         wg::gru_bwd_smem_floats(tp.HP, tp.GR, tp.bt_gb) * 4 > (size_t)wg::kMaxSmemOptin)
         return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d too large for the shared-memory BPTT kernel", H);
+    if (wg::recur_smem_floats(p.KP, p.NPR, p.GP, true) * 4 > (size_t)wg::kMaxSmemOptin)
+        return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d does not fit the shared-memory recurrence", H);
     tp.rows = (B > 0 ? B : 1) * (long long)T;
     tp.grid_gb = (int)(((B > 0 ? B : 1) + tp.bt_gb - 1) / tp.bt_gb);
     // GCN backward geometry (same station grouping as the forward)
