@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kSpThreads)
 // Row-resident variant: ONE kernel for both layers, a CTA owns one (sequence, timestep) row at a
 // time and keeps that row's whole [S, F] slab in shared memory (S * 13 * 4 B = 213 KB at S = 4096:
 // it fits beside the 17 KB of weights), so every neighbour gather is a shared-memory read and
-// HBM sees X once and U once.  Thread = station (stations tid, tid + 256, ... in groups of 4):
+// HBM sees X once and U once.  Thread = station (stations tid, tid + 512, ... two at a time):
 //   pass 1: agg = (A.X)[s] from the slab -> h = relu(agg.W1 + b1) (128 wide, registers only) ->
 //           z = h.W2; both contractions are FFMA2 on STATION pairs with the weight as the scalar
 //           operand: h2[(s, s')] += w1[f][fh] * (agg_s[f], agg_s'[f]);  z2[f][(s, s')] += w2[fh][f] * h2.
@@ -144,10 +144,13 @@ __global__ void __launch_bounds__(kSpThreads)
 //   pass 2: U[s] = relu((A.Z)[s] + b2), written row-major (coalesced); rows_to_tiles_kernel then re-lays
 //           it into the projection GEMM's K-major 128-row tiles (a 4-byte scatter from here would
 //           double the DRAM write traffic through partial sectors).
+// (Tried: stations handed out in degree order so that a warp's neighbour lists have equal length — slower,
+// 15.4 vs 13.7 ms: the CSR reads of a warp stop being contiguous.)
 // The lane = row kernels above gather from HBM with one sector per lane; at S = 4096 this
 // variant is what runs (8x fewer bytes through L2, FMA-bound instead of latency-bound).
-constexpr int kSrThreads = 256;
-constexpr int kSrGroup = 4;   // stations per thread per pass-1 group (two FFMA2 pairs)
+constexpr int kSrThreads = 512;   // 16 warps: the gather passes are latency-bound and the row pins the CTA count at 1
+constexpr int kSrGroup = 2;       // stations per thread per group (FFMA2 pairs along stations)
+constexpr int kSrPairs = kSrGroup / 2;
 
 __host__ __device__ inline size_t gcn_sparse_row_smem_bytes(int S, int Fi, int Fh, int Fo) {
     const int FS = Fi > Fo ? Fi : Fo;
@@ -204,9 +207,11 @@ __global__ void __launch_bounds__(kSrThreads, 1)
         }
         // ---- pass 1 ----
         for (int base = 0; base < S; base += kSrThreads * kSrGroup) {
-            float2 ag[FW][2];
+            float2 ag[FW][kSrPairs];
 #pragma unroll
-            for (int f = 0; f < FW; ++f) ag[f][0] = ag[f][1] = make_float2(0.0f, 0.0f);
+            for (int f = 0; f < FW; ++f)
+#pragma unroll
+                for (int q = 0; q < kSrPairs; ++q) ag[f][q] = make_float2(0.0f, 0.0f);
             // the four stations' neighbour lists are walked together (four independent load chains
             // per step; a finished list contributes a = 0 against slab row 0)
             int eb[kSrGroup], en[kSrGroup], nmax = 0;
@@ -238,12 +243,16 @@ __global__ void __launch_bounds__(kSrThreads, 1)
                     }
                 }
             }
-            float2 z[FW][2];
+            float2 z[FW][kSrPairs];
 #pragma unroll
-            for (int f = 0; f < FW; ++f) z[f][0] = z[f][1] = make_float2(0.0f, 0.0f);
+            for (int f = 0; f < FW; ++f)
+#pragma unroll
+                for (int q = 0; q < kSrPairs; ++q) z[f][q] = make_float2(0.0f, 0.0f);
 #pragma unroll 2
             for (int fh = 0; fh < Fh; ++fh) {
-                float2 h0 = make_float2(0.0f, 0.0f), h1 = make_float2(0.0f, 0.0f);
+                float2 h[kSrPairs];
+#pragma unroll
+                for (int q = 0; q < kSrPairs; ++q) h[q] = make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int v = 0; v < kSpF / 4; ++v) {
                     const float4 w = *reinterpret_cast<const float4*>(w1t + fh * kSpF + 4 * v);
@@ -251,15 +260,19 @@ __global__ void __launch_bounds__(kSrThreads, 1)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (4 * v + j < FW) {
-                            h0 = __ffma2_rn(make_float2(wv[j], wv[j]), ag[4 * v + j][0], h0);
-                            h1 = __ffma2_rn(make_float2(wv[j], wv[j]), ag[4 * v + j][1], h1);
+#pragma unroll
+                            for (int q = 0; q < kSrPairs; ++q)
+                                h[q] = __ffma2_rn(make_float2(wv[j], wv[j]), ag[4 * v + j][q], h[q]);
                         }
                     }
                 }
                 const float bb = b1s[fh];
-                h0.x += bb; h0.y += bb; h1.x += bb; h1.y += bb;
-                h0.x = h0.x < 0.0f ? 0.0f : h0.x; h0.y = h0.y < 0.0f ? 0.0f : h0.y;   // ReLU of layer 1
-                h1.x = h1.x < 0.0f ? 0.0f : h1.x; h1.y = h1.y < 0.0f ? 0.0f : h1.y;
+#pragma unroll
+                for (int q = 0; q < kSrPairs; ++q) {
+                    h[q].x += bb; h[q].y += bb;
+                    h[q].x = h[q].x < 0.0f ? 0.0f : h[q].x;   // ReLU of layer 1
+                    h[q].y = h[q].y < 0.0f ? 0.0f : h[q].y;
+                }
 #pragma unroll
                 for (int v = 0; v < kSpF / 4; ++v) {
                     const float4 w = *reinterpret_cast<const float4*>(w2p + fh * kSpF + 4 * v);
@@ -267,8 +280,9 @@ __global__ void __launch_bounds__(kSrThreads, 1)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (4 * v + j < FW) {
-                            z[4 * v + j][0] = __ffma2_rn(make_float2(wv[j], wv[j]), h0, z[4 * v + j][0]);
-                            z[4 * v + j][1] = __ffma2_rn(make_float2(wv[j], wv[j]), h1, z[4 * v + j][1]);
+#pragma unroll
+                            for (int q = 0; q < kSrPairs; ++q)
+                                z[4 * v + j][q] = __ffma2_rn(make_float2(wv[j], wv[j]), h[q], z[4 * v + j][q]);
                         }
                     }
                 }
