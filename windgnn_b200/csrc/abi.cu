@@ -479,6 +479,8 @@ struct TrainPlan {
     size_t smem_gcn;
     int splits_hh_a, splits_hh_b, splits_ih;
     int ldu, KPd, NPd;  // dU row stride (I rounded up to 4); K / N of the dU GEMM padded for inproj_kernel
+    int mt_ih, kt_per_ih;  // dW_ih on inproj_splitk_kernel: 128-row tiles of the gate dimension, k-tiles per split
+    size_t off_acb, off_bcb;
     size_t off_gates, off_dg, off_dgt, off_wpb, off_zb, off_du, off_biasp, off_gcnp, off_splitk, total;
 };
 
@@ -539,7 +541,6 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
     tp.grid_gcn = (int)(nblk < wg::kNumSMs ? nblk : wg::kNumSMs);
     tp.splits_hh_a = pick_splits(2 * H, H, tp.rows);
     tp.splits_hh_b = pick_splits(H, H, tp.rows);
-    tp.splits_ih = pick_splits(p.I, p.G, tp.rows);
     size_t o = p.total;
     tp.off_gates = o; o = align_up(o + (size_t)tp.rows * tp.LD4 * 4);
     tp.off_dg = o;    o = align_up(o + (size_t)tp.rows * tp.LD4 * 4);
@@ -548,13 +549,22 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
         tp.off_dgt = o; o = align_up(o + rt * tp.KPd * 4);            // dGI in K-major 128-row tiles
         tp.off_wpb = o; o = align_up(o + (size_t)tp.NPd * tp.KPd * 4);  // w_ih packed for dU = dGI . w_ih
         tp.off_zb = o;  o = align_up(o + (size_t)tp.NPd * 4);           // zero bias
+        tp.mt_ih = (p.G + wg::kIpBM - 1) / wg::kIpBM;
+        tp.off_acb = o; o = align_up(o + (size_t)tp.mt_ih * rt * wg::kIpBM * 4);   // dGI as column blocks [g/128][row][128]
+        tp.off_bcb = o; o = align_up(o + rt * (size_t)tp.NPd * 4);                  // U as column blocks [i/64][row][64]
+        const long long ktall = (long long)(rt / wg::kIpBK);
+        long long sp = (4LL * wg::kNumSMs) / ((long long)tp.mt_ih * (tp.NPd / wg::kIpBN));   // one wave at 4 CTAs per SM
+        if (sp < 1) sp = 1;
+        if (sp > ktall) sp = ktall;
+        tp.splits_ih = (int)sp;
+        tp.kt_per_ih = (int)((ktall + sp - 1) / sp);
     }
     tp.off_du = o;    o = align_up(o + (size_t)tp.rows * tp.ldu * 4);
     tp.off_biasp = o; o = align_up(o + (size_t)tp.grid_gb * 2 * tp.LD4 * 4);
     tp.off_gcnp = o;  o = align_up(o + (size_t)tp.grid_gcn * (wg::kGbwThreads / 16) * (2 * 256 + 32) * 4);
     size_t sk = (size_t)tp.splits_hh_a * 2 * H * H;
     if ((size_t)tp.splits_hh_b * H * H > sk) sk = (size_t)tp.splits_hh_b * H * H;
-    if ((size_t)tp.splits_ih * p.I * p.G > sk) sk = (size_t)tp.splits_ih * p.I * p.G;
+    if ((size_t)tp.splits_ih * p.G * tp.ldu > sk) sk = (size_t)tp.splits_ih * p.G * tp.ldu;
     tp.off_splitk = o; o = align_up(o + sk * 4);
     tp.total = o;
     return WG_OK;
@@ -576,7 +586,7 @@ int splitk_gemm(const wg::SgOperand& A, const wg::SgOperand& Bo, long long M, in
     WG_CUDA(cudaGetLastError());
     const long long total = M * N;
     const unsigned rgrid = (unsigned)((total + 255) / 256 < 4 * wg::kNumSMs ? (total + 255) / 256 : 4 * wg::kNumSMs);
-    wg::sg_reduce_kernel<<<rgrid, 256, 0, st>>>(part, splits, M, N, out, s_m, s_n);
+    wg::sg_reduce_kernel<<<rgrid, 256, 0, st>>>(part, splits, M, N, out, s_m, s_n, N);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -976,11 +986,29 @@ int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, c
         if ((rc = splitk_gemm(a_n, hprev, H, H, rows, tp.splits_hh_b, skp, d_whh + 2 * (size_t)H * H, H, 1, st)))
             return rc;
     }
-    // 3. dW_ih^T [I x 3H] = U^T . dGI   (U in the forward's K-major tiles), written transposed
+    // 3. dW_ih [3H x I] = dGI^T . U on the projection kernel's split-K variant: both operands re-laid as
+    //    column blocks (the contraction runs over the B*T rows), one wave of CTAs, fixed-order reduction
     {
-        const wg::SgOperand a_u{ws_ptr<float>(workspace, p.off_u), p.IP, 1, 1, 1, 0};
-        const wg::SgOperand b_dg{DG, tp.LD4, 0, 0, dg_vec, 0};
-        if ((rc = splitk_gemm(a_u, b_dg, p.I, p.G, rows, tp.splits_ih, skp, d_wih, 1, p.I, st))) return rc;
+        const long long rt = (rows + wg::kUTileRows - 1) / wg::kUTileRows * wg::kUTileRows;
+        float* acb = ws_ptr<float>(workspace, tp.off_acb);
+        float* bcb = ws_ptr<float>(workspace, tp.off_bcb);
+        wg::rows_to_colblocks_kernel<<<wg::kNumSMs * 8, 256, 0, st>>>(DG, acb, rows, rt, p.G, tp.LD4, wg::kIpBM, tp.mt_ih);
+        WG_CUDA(cudaGetLastError());
+        const dim3 tg((unsigned)(tp.NPd / 32), (unsigned)(rt / 32));
+        if (tg.y > 65535u) return fail(WG_ERR_UNSUPPORTED, "training: B*T = %lld rows exceed one pass", rows);
+        wg::tiles_to_colblocks_kernel<<<tg, 256, 0, st>>>(ws_ptr<float>(workspace, p.off_u), bcb, rows, rt, p.IP);
+        WG_CUDA(cudaGetLastError());
+        const int n_tiles = tp.NPd / wg::kIpBN;
+        WG_CUDA(cudaFuncSetAttribute(wg::inproj_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     wg::kIpSmemBytes));
+        const dim3 grid((unsigned)(tp.mt_ih * n_tiles), (unsigned)tp.splits_ih);
+        wg::inproj_splitk_kernel<<<grid, wg::kIpThreads, wg::kIpSmemBytes, st>>>(acb, bcb, skp, p.G, rt, tp.ldu, n_tiles,
+                                                                                tp.kt_per_ih);
+        WG_CUDA(cudaGetLastError());
+        const long long total = (long long)p.G * p.I;
+        wg::sg_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(skp, tp.splits_ih, p.G, p.I, d_wih, p.I, 1,
+                                                                             tp.ldu);
+        WG_CUDA(cudaGetLastError());
     }
     // 4. dU [BT x I] = dGI . W_ih on the forward's projection kernel (bulk-copy pipeline, 87 % of the FMA
     //    peak): dGI re-laid into K-major 128-row tiles, w_ih packed as [N/64][K][64], zero bias

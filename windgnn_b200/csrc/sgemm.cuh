@@ -195,14 +195,17 @@ __global__ void __launch_bounds__(kSgThreads, 2)
 
 // out[m * s_m + n * s_n] = sum_z part[z][m][n], z ascending (deterministic); also used to finish
 // column sums (M == 1).
+// ldp: row stride of the partial matrices (>= N).
 __global__ void sg_reduce_kernel(const float* __restrict__ part, int splits, long long M, int N,
-                                 float* __restrict__ out, long long s_m, long long s_n) {
+                                 float* __restrict__ out, long long s_m, long long s_n, int ldp) {
     const long long total = M * N;
+    const size_t zstride = (size_t)M * ldp;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
-        float s = 0.0f;
-        for (int z = 0; z < splits; ++z) s += part[(size_t)z * total + e];
         const long long m = e / N, n = e - m * N;
+        const float* pz = part + (size_t)m * ldp + n;
+        float s = 0.0f;
+        for (int z = 0; z < splits; ++z) s += pz[(size_t)z * zstride];
         out[m * s_m + n * s_n] = s;
     }
 }
