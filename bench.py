@@ -460,7 +460,7 @@ def main():
                       "what": "forward (gates saved) + MSE + BPTT/GEMM/GCN backward + "
                               + ("NCCL sum all-reduce of one flat 167,440-float gradient bucket + " if world > 1 else "")
                               + "fused Adam, all inside the timed region; FP32",
-                      "gpu_launches_per_step": 24 + (1 if world > 1 else 0)}
+                      "gpu_launches_per_step": 22 + (1 if world > 1 else 0)}
         del trainer, tmodel, xt, yt_
     barrier()
 
