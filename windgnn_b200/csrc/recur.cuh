@@ -398,8 +398,8 @@ namespace wg {
 // training configuration.  When the batch does not fill the SMs at 32 per CTA this kernel runs
 // instead: same data flow (W_hh^T resident in shared memory, gi of the next step prefetched with
 // cp.async, h kept in shared memory), but a CTA owns only 4 sequences, so a step is a
-// [4 x H].[H x 3H] product (thread tile 2 sequences x 4 gate columns, FFMA2) + 408 gate items and
-// takes well under a microsecond.
+// [4 x H].[H x 3H] product (thread tile 4 sequences x 2 gate columns, FFMA2) + 408 gate items and
+// takes a few microseconds.
 //
 // Every output's sum runs over k = 0 .. KP-1 ascending in ONE FFMA chain, and the merge / gate
 // expressions are the ones of gru_recur_kernel, so both kernels produce bit-identical results
@@ -412,7 +412,7 @@ __host__ __device__ inline size_t recur_small_smem_floats(int KP, int NP, int GP
     size_t n = (size_t)KP * NP;            // W_hh^T
     n += (size_t)kRsBT * (KP + 4);         // hs
     n += 2 * (size_t)kRsBT * GP;           // gi tiles (double buffered)
-    n += (size_t)kRsBT * KP;               // gh of the n gate
+    n += (size_t)kRsBT * NP;               // gh = h . W_hh^T of the current step
     n += (size_t)KP;                       // b_hn
     return n;
 }
@@ -427,8 +427,8 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     float* Ws = smem;                          // [KP][NP]
     float* hs = Ws + (size_t)KP * NP;          // [4][RS]
     float* gis = hs + kRsBT * RS;              // [2][4][ldg]
-    float* ghn = gis + 2 * kRsBT * ldg;        // [4][KP]
-    float* bns = ghn + kRsBT * KP;             // [KP]
+    float* ghs = gis + 2 * kRsBT * ldg;        // [4][NP]
+    float* bns = ghs + kRsBT * NP;             // [KP]
     const int tid = threadIdx.x;
     const long long b0 = (long long)blockIdx.x * kRsBT;
     const int H2 = 2 * H, G = 3 * H;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     }
     for (int e = tid; e < kRsBT * RS; e += kRsThreads) hs[e] = 0.0f;
     for (int e = tid; e < 2 * kRsBT * ldg; e += kRsThreads) gis[e] = 0.0f;
-    for (int e = tid; e < kRsBT * KP; e += kRsThreads) ghn[e] = 0.0f;
+    for (int e = tid; e < kRsBT * NP; e += kRsThreads) ghs[e] = 0.0f;
     for (int e = tid; e < KP; e += kRsThreads) bns[e] = e < H ? __ldg(bhn + e) : 0.0f;
 
     // gi rows of step t -> buffer (t & 1): 16-byte chunks (ldg is a multiple of 4, rows 16-byte aligned)
@@ -459,64 +459,78 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     __syncthreads();
     prefetch(0);
 
-    // GEMM coordinates: row pair rp (sequences 2 rp, 2 rp + 1), column quad cq
-    const int n_cq = NP >> 2;
-    const int rp = tid / n_cq, cq = tid - rp * n_cq;
-    const bool gemm_thread = rp < kRsBT / 2 && b0 + 2 * rp < B;   // a row pair beyond the batch does no work
+    // GEMM coordinates: every thread of the first NP / 2 owns one gate-column pair for all 4 sequences
+    const int cp = tid;
+    const bool gemm_thread = cp < (NP >> 1);
 
     for (int t = 0; t < T; ++t) {
         if (t + 1 < T) prefetch(t + 1);
-        float* g = gis + (t & 1) * kRsBT * ldg;
-        float2 acc[2][2];
-        acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = make_float2(0.0f, 0.0f);
-        if (gemm_thread && t > 0) {   // h_{-1} = 0: the product is zero at t == 0
-            const float* hp = hs + (2 * rp) * RS;
-            const float* wp = Ws + cq * 4;
+        const float* g = gis + (t & 1) * kRsBT * ldg;
+        if (gemm_thread) {
+            float2 acc[kRsBT];
+#pragma unroll
+            for (int i = 0; i < kRsBT; ++i) acc[i] = make_float2(0.0f, 0.0f);
+            if (t > 0) {   // h_{-1} = 0: the product is zero at t == 0
+                const float* wp = Ws + 2 * cp;
 #pragma unroll 2
-            for (int k = 0; k < KP; k += 4) {
-                const float4 h0 = *reinterpret_cast<const float4*>(hp + k);
-                const float4 h1 = *reinterpret_cast<const float4*>(hp + RS + k);
-                float4 w[4];
+                for (int k = 0; k < KP; k += 4) {
+                    float4 h[kRsBT];
+                    float2 w[4];
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(wp + (size_t)(k + kk) * NP);
+                    for (int i = 0; i < kRsBT; ++i) h[i] = *reinterpret_cast<const float4*>(hs + i * RS + k);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const float a0 = kk == 0 ? h0.x : kk == 1 ? h0.y : kk == 2 ? h0.z : h0.w;
-                    const float a1 = kk == 0 ? h1.x : kk == 1 ? h1.y : kk == 2 ? h1.z : h1.w;
-                    acc[0][0] = __ffma2_rn(make_float2(a0, a0), make_float2(w[kk].x, w[kk].y), acc[0][0]);
-                    acc[0][1] = __ffma2_rn(make_float2(a0, a0), make_float2(w[kk].z, w[kk].w), acc[0][1]);
-                    acc[1][0] = __ffma2_rn(make_float2(a1, a1), make_float2(w[kk].x, w[kk].y), acc[1][0]);
-                    acc[1][1] = __ffma2_rn(make_float2(a1, a1), make_float2(w[kk].z, w[kk].w), acc[1][1]);
+                    for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float2*>(wp + (size_t)(k + kk) * NP);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                        for (int i = 0; i < kRsBT; ++i) {
+                            const float a = kk == 0 ? h[i].x : kk == 1 ? h[i].y : kk == 2 ? h[i].z : h[i].w;
+                            acc[i] = __ffma2_rn(make_float2(a, a), w[kk], acc[i]);
+                        }
+                    }
                 }
             }
+#pragma unroll
+            for (int i = 0; i < kRsBT; ++i) *reinterpret_cast<float2*>(ghs + i * NP + 2 * cp) = acc[i];
         }
         // gi(t) was committed one step ago (or before the loop); only step t+1's group may still be in flight
         if (t + 1 < T) cp_async_wait<1>(); else cp_async_wait<0>();
-        __syncthreads();   // gi(t) complete for every thread (each waited for its own copies)
-        if (gemm_thread) {
-            // merge: r / z columns accumulate onto gi, the n-gate part of gh is kept apart (r multiplies it)
-            const int n0 = cq * 4;
+        __syncthreads();   // gi(t) and gh(t) complete
+        // gates: one (sequence, hidden unit) item per thread-slot, lanes along the hidden index; gi + gh is the
+        // same single addition the throughput kernel's merge performs
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                float* gr = g + (2 * rp + i) * ldg;
-                float* gn = ghn + (2 * rp + i) * KP;
-                const float a[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int n = n0 + c;
-                    if (n < H2) gr[n] += a[c];
-                    else if (n < G) gn[n - H2] = a[c];
+        for (int u = 0; u < (kRsBT * 128 + kRsThreads - 1) / kRsThreads; ++u) {
+            const int e = tid + u * kRsThreads;
+            if (e < kRsBT * H) {
+                const int b = e / H, j = e - b * H;
+                const float* gr = g + b * ldg + j;
+                const float* gh = ghs + b * NP + j;
+                const float r = sigmoid_f(gr[0] + gh[0]);
+                const float z = sigmoid_f(gr[H] + gh[H]);
+                const float hn = gh[H2] + bns[j];
+                const float n = tanh_f(gr[H2] + r * hn);
+                const float hnew = (hs[b * RS + j] - n) * z + n;
+                hs[b * RS + j] = hnew;
+                if (b0 + b < B) {
+                    out[((size_t)(b0 + b) * T + t) * H + j] = hnew;
+                    if (SAVE) {
+                        float* gs = gsave + ((size_t)(b0 + b) * T + t) * ldsave + j;
+                        gs[0] = r;
+                        gs[H] = z;
+                        gs[H2] = n;
+                        gs[H2 + H] = hn;
+                    }
                 }
             }
         }
-        __syncthreads();
-        // gates: one (sequence, hidden unit) item per thread-slot, lanes along the hidden index
-        for (int e = tid; e < kRsBT * H; e += kRsThreads) {
+        for (int e = tid + ((kRsBT * 128 + kRsThreads - 1) / kRsThreads) * kRsThreads; e < kRsBT * H; e += kRsThreads) {
+            // H > 128: the remaining items (not unrolled)
             const int b = e / H, j = e - b * H;
             const float* gr = g + b * ldg + j;
-            const float r = sigmoid_f(gr[0]);
-            const float z = sigmoid_f(gr[H]);
-            const float hn = ghn[b * KP + j] + bns[j];
+            const float* gh = ghs + b * NP + j;
+            const float r = sigmoid_f(gr[0] + gh[0]);
+            const float z = sigmoid_f(gr[H] + gh[H]);
+            const float hn = gh[H2] + bns[j];
             const float n = tanh_f(gr[H2] + r * hn);
             const float hnew = (hs[b * RS + j] - n) * z + n;
             hs[b * RS + j] = hnew;
@@ -531,7 +545,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
                 }
             }
         }
-        __syncthreads();   // h(t) visible before the next GEMM; gi buffer (t & 1) free for step t + 2
+        __syncthreads();   // h(t) visible before the next GEMM; gi buffer (t & 1) and gh free again
     }
 }
 
