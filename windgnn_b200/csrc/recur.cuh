@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     float* bns = ghs + kRsBT * NP;             // [KP]
     const int tid = threadIdx.x;
     const long long b0 = (long long)blockIdx.x * kRsBT;
-    const int H2 = 2 * H, G = 3 * H;
+    const int H2 = 2 * H;
 
     {
         const int n4 = KP * NP / 4;
@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(kRsThreads, 1)
         if (t + 1 < T) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();   // gi(t) and gh(t) complete
         // gates: one (sequence, hidden unit) item per thread-slot, lanes along the hidden index; gi + gh is the
-        // same single addition the throughput kernel's merge performs
+        // same single addition the throughput kernel's merge performs.  H <= 128 here (the launcher requires
+        // NP / 2 <= kRsThreads), so the unrolled slots cover every item
 #pragma unroll
         for (int u = 0; u < (kRsBT * 128 + kRsThreads - 1) / kRsThreads; ++u) {
             const int e = tid + u * kRsThreads;
@@ -520,28 +521,6 @@ __global__ void __launch_bounds__(kRsThreads, 1)
                         gs[H2] = n;
                         gs[H2 + H] = hn;
                     }
-                }
-            }
-        }
-        for (int e = tid + ((kRsBT * 128 + kRsThreads - 1) / kRsThreads) * kRsThreads; e < kRsBT * H; e += kRsThreads) {
-            // H > 128: the remaining items (not unrolled)
-            const int b = e / H, j = e - b * H;
-            const float* gr = g + b * ldg + j;
-            const float* gh = ghs + b * NP + j;
-            const float r = sigmoid_f(gr[0] + gh[0]);
-            const float z = sigmoid_f(gr[H] + gh[H]);
-            const float hn = gh[H2] + bns[j];
-            const float n = tanh_f(gr[H2] + r * hn);
-            const float hnew = (hs[b * RS + j] - n) * z + n;
-            hs[b * RS + j] = hnew;
-            if (b0 + b < B) {
-                out[((size_t)(b0 + b) * T + t) * H + j] = hnew;
-                if (SAVE) {
-                    float* gs = gsave + ((size_t)(b0 + b) * T + t) * ldsave + j;
-                    gs[0] = r;
-                    gs[H] = z;
-                    gs[H2] = n;
-                    gs[H2 + H] = hn;
                 }
             }
         }
