@@ -96,7 +96,8 @@ int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, con
 /* Same computation with HOST buffers for x (pinned for full overlap) and out: the batch is
  * streamed through the device in `chunk`-sized pieces, H2D copy / compute / D2H copy of
  * consecutive pieces overlapped on internal streams (two compute lanes, so the latency-bound
- * recurrence of one piece overlaps the GCN / projection of the next).  Parameters and adj are device
+ * recurrence of one piece overlaps the GCN / projection of the next).  `chunk` = 0 selects pieces of
+ * 256 sequences.  Parameters and adj are device
  * pointers (they are the model, resident on the GPU as in src/main.py:27,43).  Blocks
  * until `out_host` is complete.  Replaces the per-window loop of src/main.py:101-103
  * (`model(adj, batch_x)` followed by `.cpu()`). */

@@ -50,7 +50,10 @@ def test_workspace_planning():
     # the default chunk caps the scratch: 1M sequences need no more than one wave's worth
     assert lib.wg_gcn_gru_workspace_bytes(1 << 20, *dims34, 0, 0) == lib.wg_gcn_gru_workspace_bytes(148 * 32, *dims34, 0, 0)
     assert lib.wg_gcn_gru_workspace_bytes(1 << 20, *dims34, 1024, 0) < big
-    assert lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 0, 0) > big
+    # host-buffer path: two compute lanes + three staging slots each for x and out; chunk 0 = pieces of 256
+    assert lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 4096, 0) > 2 * big
+    assert lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 0, 0) == lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 256, 0)
+    assert lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 0, 0) < big
     # the tensor-core path keeps U and w_ih as hi + lo parts: more scratch; unknown flags are rejected
     assert lib.wg_gcn_gru_workspace_bytes(4096, *dims34, 0, _lib.FLAG_TENSOR_CORES) > big
     assert lib.wg_gcn_gru_workspace_bytes(4096, *dims34, 0, 8) == 0

@@ -757,10 +757,12 @@ int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, con
 // workspace = [ compute workspace 0 | compute workspace 1 | x staging 0..2 | out staging 0..2 ]
 constexpr int kHostLanes = 2;
 constexpr int kHostSlots = 3;
+constexpr long long kHostDefaultChunk = 256;   // measured best piece size for the 34-station model
 
 size_t wg_gcn_gru_host_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
                                        int64_t chunk, int flags) {
     Plan p;
+    if (chunk == 0) chunk = kHostDefaultChunk;   // the host path pipelines: a piece small enough to overlap copies
     if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, false, flags)) return 0;
     const size_t xs = align_up((size_t)p.chunk * T * S * F_in * 4);
     const size_t os = align_up((size_t)p.chunk * T * H * 4);
@@ -773,6 +775,7 @@ int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const flo
                                 int S, int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags,
                                 void* workspace, size_t workspace_bytes, int device) {
     Plan p;
+    if (chunk == 0) chunk = kHostDefaultChunk;
     int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, false, flags);
     if (rc) return rc;
     if (B == 0) return WG_OK;
