@@ -432,6 +432,24 @@ def main():
             model.precision = args.precision
     barrier()
 
+    # ---------------- the reference's own call pattern: one window per call (src/main.py:101-103) ----------
+    batch1 = None
+    if rank == 0:
+        with torch.no_grad():
+            x1 = x[:1]
+            for _ in range(5):
+                model(adj, x1)
+            torch.cuda.synchronize(dev)
+            b0e, b1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0e.record()
+            for _ in range(50):
+                y1 = model(adj, x1)
+            b1e.record()
+            torch.cuda.synchronize(dev)
+        batch1 = {"gpu_ms_per_window": b0e.elapsed_time(b1e) / 50,
+                  "what": "model(adj_matrix, batch_x) with batch_x [1,168,34,13] resident on the GPU, 50 calls back to back"}
+    barrier()
+
     # ---------------- training step (BASELINE.json configs[4]): fwd + MSE + bwd + all-reduce + Adam ----------
     train_step = None
     if not args.no_train_step:
@@ -558,6 +576,16 @@ def main():
             v, threads, reps, secs = cpu_port_seq_per_s(sd, adj_cpu, n_seq=2048, min_seconds=12.0, max_reps=40)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{reps} x 2048 sequences of the same workload in {secs:.1f} s, torch CPU fp32"}
+            if batch1 is not None:   # the same port called the way the reference calls its model: one window at a time
+                from oracle import gcn_gru_forward_torch
+
+                x1c = torch.rand((1, T, S, F))
+                for _ in range(3):
+                    gcn_gru_forward_torch(adj_cpu, x1c, sd)
+                t0 = time.perf_counter()
+                for _ in range(30):
+                    gcn_gru_forward_torch(adj_cpu, x1c, sd)
+                batch1["cpu_port_ms_per_window"] = (time.perf_counter() - t0) / 30 * 1e3
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -571,6 +599,7 @@ def main():
                        "station_sequence_predictions_per_s": value * S},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * steps,
             "roofline": roofline, "cpu_baseline": cpu, "tensor_path": tensor_path, "train_step": train_step,
+            "batch1": batch1,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
