@@ -6,15 +6,18 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gcn.cuh"
 #include "gcn_bwd.cuh"
+#include "gcn_rows.cuh"
 #include "gcn_sparse.cuh"
 #include "gru_bwd.cuh"
 #include "inproj.cuh"
 #include "inproj_tc.cuh"
 #include "recur.cuh"
+#include "recur_unit.cuh"
 #include "sgemm.cuh"
 #include "train_misc.cuh"
 #include "wg_common.cuh"
@@ -70,7 +73,7 @@ struct Plan {
     bool tc;       // tensor-core (3xTF32 tcgen05) input projection: U and w_ih kept as hi + lo
     wg::TcShape tcs;
     size_t off_u_lo, off_wp_lo;
-    size_t off_wp, off_bias, off_wht, off_bhn, off_u, off_gi, off_z, total;
+    size_t off_wp, off_bias, off_wht, off_whu, off_bhn, off_u, off_gi, off_z, total;
 };
 
 long long default_chunk(long long B, size_t bytes_per_seq) {
@@ -117,6 +120,8 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     p.off_wp_lo = o; if (p.tc) o = align_up(o + (size_t)wrows * p.IP * 4);
     p.off_bias = o; o = align_up(o + (size_t)(wrows > 512 ? wrows : 512) * 4);
     p.off_wht = o;  o = align_up(o + (size_t)p.KP * p.NPR * 4);
+    p.off_whu = o;  // [k][gate][unit] (recur_unit.cuh), only for hidden sizes that kernel serves
+    if (wg::recur_u_applies(H)) o = align_up(o + (size_t)p.KP * 3 * wg::recur_u_hp2(H) * 4);
     p.off_bhn = o;  o = align_up(o + (size_t)p.KP * 4);
     const size_t rows = (size_t)p.chunk * T;
     const size_t rows_tiled = (rows + wg::kUTileRows - 1) / wg::kUTileRows * wg::kUTileRows;
@@ -148,8 +153,8 @@ T* ws_ptr(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>
 __global__ void pack_params_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                    const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                                    float* __restrict__ wp, float* __restrict__ wp_lo, float* __restrict__ bias,
-                                   float* __restrict__ wht, float* __restrict__ bhn, int I, int H, int IP,
-                                   int NPB, int KP, int NPR, int tc_np, int tc_ne, int n_bias) {
+                                   float* __restrict__ wht, float* __restrict__ whu, float* __restrict__ bhn, int I,
+                                   int H, int IP, int NPB, int KP, int NPR, int tc_np, int tc_ne, int n_bias) {
     const int G = 3 * H;
     const long long n_wp = tc_np > 0 ? (long long)tc_np * IP : (long long)NPB * IP;
     const long long n_wht = (long long)KP * NPR;
@@ -181,6 +186,16 @@ __global__ void pack_params_kernel(const float* __restrict__ w_ih, const float* 
     for (long long e = t0; e < n_wht; e += stride) {
         const int k = (int)(e / NPR), n = (int)(e % NPR);
         wht[e] = (k < H && n < G) ? w_hh[(size_t)n * H + k] : 0.0f;
+    }
+    if (whu != nullptr) {   // W_hh^T for the unit-tiled recurrence: whu[k][g][j] = w_hh[g*H + j][k]
+        const int HP2 = wg::recur_u_hp2(H);
+        const long long n_whu = (long long)KP * 3 * HP2;
+        for (long long e = t0; e < n_whu; e += stride) {
+            const int j = (int)(e % HP2);
+            const long long r = e / HP2;
+            const int g = (int)(r % 3), k = (int)(r / 3);
+            whu[e] = (k < H && j < H) ? w_hh[((size_t)g * H + j) * H + k] : 0.0f;
+        }
     }
     for (long long e = t0; e < n_bias; e += stride) {
         float v = 0.0f;
@@ -240,10 +255,33 @@ int pick_sg(int S) {
     return wg::ceil_div(S, 7) * 7 <= wg::ceil_div(S, 4) * 4 ? 7 : 4;
 }
 
+bool force_legacy();
+
+// second-generation fused two-layer kernel (gcn_rows.cuh): lane = row, output straight into the tiles
+int launch_gcn_rows(const float* X, const float* adj, const float* W1, const float* b1, const float* W2,
+                    const float* b2, float* out, long long R, int S, int ldo, cudaStream_t st) {
+    const size_t smem = wg::gcn_rows_smem_floats(S) * 4;
+    const int threads = wg::gcn_rows_warps(S) * 32;
+    WG_CUDA(cudaFuncSetAttribute(wg::gcn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    WG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wg::gcn_rows_kernel, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long nblocks = (R + wg::kGrRows - 1) / wg::kGrRows;
+    long long grid = (long long)wg::kNumSMs * per_sm;
+    if (grid > nblocks) grid = nblocks;
+    if (grid < 1) return WG_OK;
+    wg::gcn_rows_kernel<<<(unsigned)grid, threads, smem, st>>>(X, adj, W1, b1, W2, b2, out, R, S, ldo);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
 template <int LAYERS, bool TILED>
 int launch_gcn(const float* X, const float* adj, const float* W1, const float* b1, const float* W2,
                const float* b2, float* out, float* out_lo, long long R, int S, int Fi, int Fh, int Fo, int ldo,
                cudaStream_t st) {
+    if (LAYERS == 2 && TILED && out_lo == nullptr && wg::gcn_rows_applies(S, Fi, Fh, Fo) && !force_legacy() &&
+        wg::gcn_rows_smem_floats(S) * 4 <= (size_t)wg::kMaxSmemOptin)
+        return launch_gcn_rows(X, adj, W1, b1, W2, b2, out, R, S, ldo, st);
     const int fmax = Fi > Fh ? (Fi > Fo ? Fi : Fo) : (Fh > Fo ? Fh : Fo);
 #define WG_GCN(FP, SG, EX) \
     launch_gcn_t<FP, SG, EX, LAYERS, TILED>(X, adj, W1, b1, W2, b2, out, out_lo, R, S, Fi, Fh, Fo, ldo, st)
@@ -388,9 +426,63 @@ int launch_recur_small(const Plan& p, void* ws, float* out, long long Bc, cudaSt
     return WG_OK;
 }
 
+// ---- second-generation throughput recurrence (recur_unit.cuh) ----
+}  // namespace
+namespace {
+bool force_legacy() {   // testing knob: WG_FORCE_LEGACY=1 selects the first-generation kernels (bit-identical results)
+    const char* e = getenv("WG_FORCE_LEGACY");
+    return e && e[0] == '1';
+}
+// sequences per group: the R in [4, 8] that needs the fewest (waves x R) for this batch
+int recur_u_pick_r(long long Bc, int ngrp) {
+    int best = wg::kRuMaxR;
+    long long best_cost = -1;
+    for (int r = wg::kRuMaxR; r >= wg::kRuMinR; --r) {
+        const long long ctas = (Bc + (long long)ngrp * r - 1) / ((long long)ngrp * r);
+        const long long waves = (ctas + wg::kNumSMs - 1) / wg::kNumSMs;
+        const long long cost = waves * (r + 1);   // +1: the per-step work that does not shrink with R
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = r; }
+    }
+    return best;
+}
+bool recur_unit_applies(const Plan& p) {
+    return !force_legacy() && wg::recur_u_applies(p.H) &&
+           wg::recur_u_smem_floats(p.H, wg::kRuMinR) * 4 <= (size_t)wg::kMaxSmemOptin;
+}
+template <int R, int WPG, bool SAVE>
+int launch_recur_unit_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
+    const size_t smem = wg::recur_u_smem_floats(p.H, R) * 4;
+    auto kern = wg::gru_recur_unit_kernel<R, WPG, SAVE>;
+    WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_cta = (wg::kRuWarps / WPG) * R;
+    const long long grid = (Bc + per_cta - 1) / per_cta;
+    if (grid < 1) return WG_OK;
+    kern<<<(unsigned)grid, wg::kRuThreads, smem, st>>>(ws_ptr<float>(ws, p.off_gi), ws_ptr<float>(ws, p.off_whu),
+                                                      ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, p.GP, gsave,
+                                                      ldsave);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+template <bool SAVE>
+int launch_recur_unit(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
+    const int wpg = wg::recur_u_wpg(p.H);
+    int r = recur_u_pick_r(Bc, wg::kRuWarps / wpg);
+    while (r > wg::kRuMinR && wg::recur_u_smem_floats(p.H, r) * 4 > (size_t)wg::kMaxSmemOptin) --r;
+#define WG_RU(RR)                                                                                      \
+    case RR:                                                                                           \
+        return wpg == 1 ? launch_recur_unit_t<RR, 1, SAVE>(p, ws, out, Bc, st, gsave, ldsave)          \
+                        : launch_recur_unit_t<RR, 2, SAVE>(p, ws, out, Bc, st, gsave, ldsave);
+    switch (r) {
+        WG_RU(4) WG_RU(5) WG_RU(6) WG_RU(7) WG_RU(8)
+    }
+#undef WG_RU
+    return fail(WG_ERR_UNSUPPORTED, "recurrence: no kernel for R = %d", r);
+}
+
 // training forward: the same recurrence, additionally saving [r | z | n | hn] per (sequence, step)
 int launch_recur_save(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
     if (recur_small_applies(p, Bc)) return launch_recur_small<true>(p, ws, out, Bc, st, gsave, ldsave);
+    if (recur_unit_applies(p)) return launch_recur_unit<true>(p, ws, out, Bc, st, gsave, ldsave);
     const size_t smem_ws = wg::recur_smem_floats(p.KP, p.NPR, p.GP, true) * 4;
     if (smem_ws > (size_t)wg::kMaxSmemOptin)
         return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d does not fit the shared-memory recurrence", p.H);
@@ -403,6 +495,7 @@ int launch_recur_save(const Plan& p, void* ws, float* out, long long Bc, cudaStr
 
 int launch_recur(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
     if (recur_small_applies(p, Bc)) return launch_recur_small<false>(p, ws, out, Bc, st, nullptr, 0);
+    if (recur_unit_applies(p)) return launch_recur_unit<false>(p, ws, out, Bc, st, nullptr, 0);
     const size_t smem_ws = wg::recur_smem_floats(p.KP, p.NPR, p.GP, true) * 4;
     if (smem_ws <= (size_t)wg::kMaxSmemOptin) return launch_recur_ws<true>(p, ws, out, Bc, st);
     const size_t smem_nows = wg::recur_smem_floats(p.KP, p.NPR, p.GP, false) * 4;
@@ -415,8 +508,9 @@ int launch_pack(const Plan& p, void* ws, const float* w_ih, const float* w_hh, c
     const int wrows = p.tc ? (p.tcs.NP > p.NPB ? p.tcs.NP : p.NPB) : p.NPB;
     pack_params_kernel<<<wg::kNumSMs * 2, 256, 0, st>>>(
         w_ih, w_hh, b_ih, b_hh, ws_ptr<float>(ws, p.off_wp), ws_ptr<float>(ws, p.off_wp_lo),
-        ws_ptr<float>(ws, p.off_bias), ws_ptr<float>(ws, p.off_wht), ws_ptr<float>(ws, p.off_bhn), p.I, p.H, p.IP,
-        p.NPB, p.KP, p.NPR, p.tc ? p.tcs.NP : 0, p.tcs.N_each, wrows > 512 ? wrows : 512);
+        ws_ptr<float>(ws, p.off_bias), ws_ptr<float>(ws, p.off_wht),
+        wg::recur_u_applies(p.H) ? ws_ptr<float>(ws, p.off_whu) : nullptr, ws_ptr<float>(ws, p.off_bhn), p.I, p.H, p.IP, p.NPB, p.KP, p.NPR, p.tc ? p.tcs.NP : 0, p.tcs.N_each,
+        wrows > 512 ? wrows : 512);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }

@@ -1,0 +1,304 @@
+// Both GCN layers of the 13-feature model, second generation: lane = row, warp = station group.
+//
+// Reference: GraphConvLayer.forward, src/step5_gcn_layer_model.py:13-23 (matmul order :15,:18,
+// ReLU :21), chained twice by GCN_GRU.forward, src/step6_gcn_gru_combined_model.py:17,20; the
+// `.view(1, T, S*13)` of :20 is the flat column index s*13 + f of the output.
+//
+// gcn_kernel (gcn.cuh) maps a thread to (row, 7 stations): the final slab has to go back through
+// shared memory to reach the K-major tiles of the projection GEMM (a 96-byte run per store
+// instruction, ~670 instructions per thread and block), 8 of 128 lanes idle, and 53 % of the issued
+// instructions are not FMAs (ncu r01: FMA pipe 60 %).  Here
+//   * a CTA owns 32 consecutive rows (a row = one (sequence, timestep) pair = an [S, 13] slab),
+//     LANE = row; a warp owns a group of station PAIRS for all 32 rows;
+//   * aggregation  acc2[(s, s+1)][f] += x[s'][f] * (A[s][s'], A[s+1][s'])  — FFMA2 with the feature
+//     value as the broadcast scalar and the adjacency pair warp-uniform (one broadcast LDS.128 per
+//     four stations); exactly 13 features, no padded feature lane;
+//   * transform    o2[(s, s+1)][fo] += W[f][fo] * acc2[(s, s+1)][f]  — the accumulator pair IS the
+//     operand pair; the weight is a warp-uniform scalar;
+//   * layer 1 writes its result back to shared memory in a padded [row][station][16] layout
+//     (16-byte loads for layer 2, row stride = 4 mod 32 floats: conflict free);
+//   * layer 2's result goes from registers straight to the K-major tiles of the projection GEMM:
+//     for a fixed column the 32 lanes are 32 consecutive rows, i.e. one 128-byte store.
+// The input block arrives with ONE bulk async copy (cp.async.bulk), as before.
+//
+// Every sum runs in the order of gcn_kernel (s' ascending, then f ascending, bias added last), so the
+// two kernels are bit-identical (tested); this one serves F_in = F_hid = F_out = 13 (the only widths
+// the reference's forward accepts: the 13 is hard-coded at step6:16) and S <= 48.
+#pragma once
+
+#include "gcn.cuh"
+#include "wg_common.cuh"
+
+namespace wg {
+
+constexpr int kGrRows = 32;     // rows per block (= lanes)
+constexpr int kGrF = 13;        // feature width served
+constexpr int kGrFS = 16;       // feature stride of the layer-1 result in shared memory
+constexpr int kGrAP = 12;       // adjacency floats per (s', warp): up to 6 station pairs
+constexpr int kGrMaxPairs = 5;  // station pairs per warp (accumulators: 5 x 13 float2 = 130 registers)
+constexpr int kGrMaxWarps = 8;
+
+__host__ __device__ inline int gcn_rows_warps(int S) { return ceil_div(ceil_div(S, 2), kGrMaxPairs); }
+__host__ __device__ inline bool gcn_rows_applies(int S, int Fi, int Fh, int Fo) {
+    return Fi == kGrF && Fh == kGrF && Fo == kGrF && gcn_rows_warps(S) <= kGrMaxWarps && S <= 48;
+}
+__host__ __device__ inline int gcn_rows_rs2(int S) { return S * kGrFS + 4; }
+__host__ __device__ inline size_t gcn_rows_smem_floats(int S) {
+    const int NW = gcn_rows_warps(S);
+    size_t n = (size_t)S * NW * kGrAP;                 // adjW[s'][warp][12]
+    n += 2 * (size_t)kGcnFS * kGcnFS + 2 * kGcnFS;     // w1, w2, b1, b2 (zero padded 16 x 16 / 16)
+    const size_t in_f = (size_t)kGrRows * S * kGrF, g1_f = (size_t)kGrRows * gcn_rows_rs2(S);
+    n += round_up((int)(in_f > g1_f ? in_f : g1_f), 4) + 4;   // slab block (+ mbarrier)
+    return n;
+}
+
+// acc[p][f] = sum_{s'} x[s'][f] * (A[2p][s'], A[2p+1][s'])  for this warp's NPW station pairs.
+// PADDED: x row is [S][16] (layer-1 result) else [S][13] as it sits in HBM (`vec`: the row length S*13 is
+// even, so every row base is 8-byte aligned and the loads are 8 bytes wide where the offset is even).
+template <int NPW, bool PADDED>
+__device__ __forceinline__ void gr_aggregate(float2 (&acc)[NPW][kGrF], const float* __restrict__ xrow,
+                                             const float* __restrict__ arow, int astride, int S, bool vec) {
+#pragma unroll
+    for (int p = 0; p < NPW; ++p)
+#pragma unroll
+        for (int f = 0; f < kGrF; ++f) acc[p][f] = make_float2(0.0f, 0.0f);
+    auto step = [&](int sp, auto odd_tag) {
+        constexpr bool ODD = decltype(odd_tag)::value != 0;
+        float a[2 * ((NPW + 1) / 2) * 2];
+        const float* ap = arow + (size_t)sp * astride;
+#pragma unroll
+        for (int q = 0; q < (NPW + 1) / 2; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(ap + 4 * q);
+            a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w;
+        }
+        float x[kGrF];
+        if (PADDED) {
+            const float* xp = xrow + sp * kGrFS;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(xp + 4 * q);
+                x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+            }
+            x[12] = xp[12];
+        } else {
+            const float* xp = xrow + sp * kGrF;
+            if (!vec) {   // odd row length (odd S): the rows are only 4-byte aligned
+#pragma unroll
+                for (int f = 0; f < kGrF; ++f) x[f] = xp[f];
+            } else if (!ODD) {   // even offset: pairs (0,1) .. (10,11), then 12
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const float2 t = *reinterpret_cast<const float2*>(xp + 2 * q);
+                    x[2 * q] = t.x; x[2 * q + 1] = t.y;
+                }
+                x[12] = xp[12];
+            } else {      // odd offset: 0, then pairs (1,2) .. (11,12)
+                x[0] = xp[0];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const float2 t = *reinterpret_cast<const float2*>(xp + 1 + 2 * q);
+                    x[1 + 2 * q] = t.x; x[2 + 2 * q] = t.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NPW; ++p) {
+            const float2 aa = make_float2(a[2 * p], a[2 * p + 1]);
+#pragma unroll
+            for (int f = 0; f < kGrF; ++f) acc[p][f] = __ffma2_rn(make_float2(x[f], x[f]), aa, acc[p][f]);
+        }
+    };
+    int sp = 0;
+#pragma unroll 1
+    for (; sp + 1 < S; sp += 2) {
+        step(sp, IntC<0>{});
+        step(sp + 1, IntC<1>{});
+    }
+    if (sp < S) step(sp, IntC<0>{});
+}
+
+// o[p][c] = sum_f W[f][c0 + c] * acc[p][f]  for one chunk of WIDTH output features (f ascending)
+template <int NPW, int WIDTH>
+__device__ __forceinline__ void gr_transform_chunk(float2 (&o)[NPW][4], const float2 (&acc)[NPW][kGrF],
+                                                   const float* __restrict__ Wn, int c0) {
+#pragma unroll
+    for (int p = 0; p < NPW; ++p)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[p][c] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int f = 0; f < kGrF; ++f) {
+        const float4 w = *reinterpret_cast<const float4*>(Wn + f * kGcnFS + c0);
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int p = 0; p < NPW; ++p)
+#pragma unroll
+            for (int c = 0; c < WIDTH; ++c) o[p][c] = __ffma2_rn(make_float2(wv[c], wv[c]), acc[p][f], o[p][c]);
+    }
+}
+
+__device__ __forceinline__ float gr_relu(float u) { return u < 0.0f ? 0.0f : u; }   // NaN propagates like torch.relu
+
+// One row block through both layers for a warp that owns NPW station pairs starting at station s0.
+template <int NPW>
+__device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* __restrict__ arow, int astride,
+                                         const float* __restrict__ w1d, const float* __restrict__ b1s,
+                                         const float* __restrict__ w2d, const float* __restrict__ b2s, int S, int s0,
+                                         int lane, bool row_ok, float* __restrict__ out_col0, int ldo, bool pad_warp) {
+    const int in_cols = S * kGrF, RS2 = gcn_rows_rs2(S);
+    float2 acc[NPW][kGrF];
+    // ---- layer 1 ----
+    gr_aggregate<NPW, false>(acc, buf + (size_t)lane * in_cols, arow, astride, S, (in_cols & 1) == 0);
+    __syncthreads();   // every warp has finished reading the input slab: the padded layer-1 result may overwrite it
+    float* g1row = buf + (size_t)lane * RS2;
+    auto store_g1 = [&](const float2 (&o)[NPW][4], int c0) {
+        const float4 bb = *reinterpret_cast<const float4*>(b1s + c0);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int p = 0; p < NPW; ++p) {
+            const int s = s0 + 2 * p;
+            float4 v0, v1;   // columns >= 13 come out as relu(0 + 0) = 0: the padding is defined
+            v0.x = gr_relu(o[p][0].x + bv[0]); v0.y = gr_relu(o[p][1].x + bv[1]);
+            v0.z = gr_relu(o[p][2].x + bv[2]); v0.w = gr_relu(o[p][3].x + bv[3]);
+            v1.x = gr_relu(o[p][0].y + bv[0]); v1.y = gr_relu(o[p][1].y + bv[1]);
+            v1.z = gr_relu(o[p][2].y + bv[2]); v1.w = gr_relu(o[p][3].y + bv[3]);
+            if (s < S) *reinterpret_cast<float4*>(g1row + s * kGrFS + c0) = v0;
+            if (s + 1 < S) *reinterpret_cast<float4*>(g1row + (s + 1) * kGrFS + c0) = v1;
+        }
+    };
+    {
+        float2 o[NPW][4];
+#pragma unroll 1
+        for (int c0 = 0; c0 < 12; c0 += 4) {   // output features 0 .. 11
+            gr_transform_chunk<NPW, 4>(o, acc, w1d, c0);
+            store_g1(o, c0);
+        }
+        gr_transform_chunk<NPW, 1>(o, acc, w1d, 12);   // feature 12 (kGrF == 13)
+        store_g1(o, 12);
+    }
+    __syncthreads();   // layer-1 result complete
+    // ---- layer 2 ----
+    gr_aggregate<NPW, true>(acc, g1row, arow, astride, S, true);
+    __syncthreads();   // the slab may be overwritten by the next block's bulk copy
+    auto store_u = [&](const float2 (&o)[NPW][4], int c0, auto width) {
+        constexpr int W = decltype(width)::value;
+        const float4 bb = *reinterpret_cast<const float4*>(b2s + c0);
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+        if (row_ok) {
+#pragma unroll
+            for (int p = 0; p < NPW; ++p) {
+                const int s = s0 + 2 * p;
+                // column s*13 + fo of the tile: 128 floats per column, this lane's row inside it
+                float* c_lo = out_col0 + (size_t)(s * kGrF + c0) * kUTileRows;
+#pragma unroll
+                for (int c = 0; c < W; ++c) {
+                    if (s < S) c_lo[(size_t)c * kUTileRows] = gr_relu(o[p][c].x + bv[c]);
+                    if (s + 1 < S) c_lo[(size_t)(kGrF + c) * kUTileRows] = gr_relu(o[p][c].y + bv[c]);
+                }
+            }
+        }
+    };
+    {
+        float2 o[NPW][4];
+#pragma unroll 1
+        for (int c0 = 0; c0 < 12; c0 += 4) {
+            gr_transform_chunk<NPW, 4>(o, acc, w2d, c0);
+            store_u(o, c0, IntC<4>{});
+        }
+        gr_transform_chunk<NPW, 1>(o, acc, w2d, 12);
+        store_u(o, 12, IntC<1>{});
+    }
+    if (pad_warp && row_ok)   // zero the K padding of the projection GEMM
+        for (int c = in_cols; c < ldo; ++c) out_col0[(size_t)c * kUTileRows] = 0.0f;
+}
+
+// X [R][S][13] -> out [ceil(R/128)][ldo][128] (K-major row tiles, columns >= S*13 zero)
+__global__ void __launch_bounds__(kGrMaxWarps * 32, 1)
+    gcn_rows_kernel(const float* __restrict__ X, const float* __restrict__ adj, const float* __restrict__ W1,
+                    const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
+                    float* __restrict__ out, long long R, int S, int ldo) {
+    extern __shared__ __align__(16) float smem[];
+    const int NW = gcn_rows_warps(S);
+    const int nthreads = NW * 32;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int in_cols = S * kGrF;
+    // station pairs are dealt out as evenly as possible; the warps with one more pair are rotated
+    // with the CTA's wave so that co-resident CTAs do not put their heavy warps on one scheduler
+    const int NPT = ceil_div(S, 2), base = NPT / NW, extra = NPT % NW;
+    const int w = ((tid >> 5) + (blockIdx.x / kNumSMs) * 2) % NW;
+    const int npw = base + (w < extra ? 1 : 0);
+    const int p0 = w * base + (w < extra ? w : extra);
+    const int s0 = 2 * p0;
+
+    float* adjW = smem;                                   // [S][NW][12]
+    float* w1d = adjW + (size_t)S * NW * kGrAP;
+    float* w2d = w1d + kGcnFS * kGcnFS;
+    float* b1s = w2d + kGcnFS * kGcnFS;
+    float* b2s = b1s + kGcnFS;
+    float* buf = b2s + kGcnFS;
+    const size_t in_f = (size_t)kGrRows * in_cols, g1_f = (size_t)kGrRows * gcn_rows_rs2(S);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(buf + round_up((int)(in_f > g1_f ? in_f : g1_f), 4));
+
+    for (int e = tid; e < S * NW * kGrAP; e += nthreads) {
+        const int sp = e / (NW * kGrAP), c = e % (NW * kGrAP);
+        const int ww = c / kGrAP, i = c % kGrAP;
+        const int wn = base + (ww < extra ? 1 : 0), ws0 = 2 * (ww * base + (ww < extra ? ww : extra));
+        const int s = ws0 + i;
+        adjW[e] = (i < 2 * wn && s < S) ? adj[(size_t)s * S + sp] : 0.0f;
+    }
+    for (int e = tid; e < kGcnFS * kGcnFS; e += nthreads) {
+        const int f = e / kGcnFS, fo = e % kGcnFS;
+        const bool in = f < kGrF && fo < kGrF;
+        w1d[e] = in ? W1[f * kGrF + fo] : 0.0f;
+        w2d[e] = in ? W2[f * kGrF + fo] : 0.0f;
+    }
+    for (int e = tid; e < kGcnFS; e += nthreads) {
+        b1s[e] = e < kGrF ? b1[e] : 0.0f;
+        b2s[e] = e < kGrF ? b2[e] : 0.0f;
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const float* arow = adjW + w * kGrAP;
+    const int astride = NW * kGrAP;
+    const long long nblocks = (R + kGrRows - 1) / kGrRows;
+    unsigned phase = 0;
+    for (long long rb = blockIdx.x; rb < nblocks; rb += gridDim.x) {
+        const long long r0 = rb * kGrRows;
+        const int nrows = (int)((R - r0) < kGrRows ? (R - r0) : kGrRows);
+        const float* src = X + (size_t)r0 * in_cols;
+        const size_t bytes = (size_t)nrows * in_cols * 4;
+        const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0);
+        if (bulk) {
+            if (tid == 0) {
+                mbar_expect_tx(bar, (unsigned)bytes);
+                bulk_g2s(buf, src, (unsigned)bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {   // ragged / unaligned block: coalesced element copy
+            const int n_in = nrows * in_cols;
+            for (int e = tid; e < n_in; e += nthreads) buf[e] = __ldg(src + e);
+            __syncthreads();
+        }
+        const long long r = r0 + lane;
+        float* out_col0 = out + (size_t)(r / kUTileRows) * ldo * kUTileRows + (r % kUTileRows);
+        const bool row_ok = lane < nrows;
+        const bool pad_warp = w == NW - 1;
+#define WG_GR(N)                                                                                              \
+    case N:                                                                                                   \
+        gr_block<N>(buf, arow, astride, w1d, b1s, w2d, b2s, S, s0, lane, row_ok, out_col0, ldo, pad_warp);    \
+        break;
+        switch (npw) {   // warp-uniform
+            WG_GR(1) WG_GR(2) WG_GR(3) WG_GR(4) WG_GR(5)
+            default: break;
+        }
+#undef WG_GR
+        // gr_block's last barrier already separates this block's reads from the next bulk copy; the
+        // generic-proxy reads are ordered before the async-proxy write by that barrier
+    }
+}
+
+}  // namespace wg

@@ -57,9 +57,6 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-template <int N>
-struct IntC { static constexpr int value = N; };
-
 #ifndef WG_GATE_EXP
 #define WG_GATE_EXP 0
 #endif

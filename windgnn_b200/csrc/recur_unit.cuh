@@ -1,0 +1,250 @@
+// GRU recurrence, throughput kernel (second generation): gate values never leave registers.
+//
+// Reference: `gru_out, _ = self.gru(hidden2)` at src/step6_gcn_gru_combined_model.py:23 (module
+// built at :11), PyTorch gate convention (rows r, z, n) — see recur.cuh for the equations.
+//
+// gru_recur_kernel (recur.cuh) tiles the per-step product h . W_hh^T by gate COLUMNS, so the r, z
+// and n values of one hidden unit end up in different threads and have to meet in shared memory
+// (merge phase, a barrier, a separate gate phase); its two 16-sequence groups hand the FMA pipe to
+// each other, which leaves one GEMM warp per scheduler and the pipe half idle (ncu r01: 57.6 %).
+//
+// Here a thread owns the r, z and n columns of TWO hidden units (2p, 2p+1) for the R sequences of
+// its group:   acc[i][g] (float2 over the unit pair)  +=  h[i][k] * (W_g[k][2p], W_g[k][2p+1])
+// — FFMA2 with h as the broadcast scalar.  When the product is done the thread already holds
+// everything a GRU cell needs for its R x 2 (sequence, unit) items: gi arrives in thread-private
+// shared-memory slots (cp.async, issued one step ahead by the thread that consumes them), the
+// previous state of those items lives in registers.  No merge phase, no gh round trip; the only
+// exchange per step is the new state, written to the other half of a double-buffered h tile,
+// followed by ONE named barrier among the group's warps.
+//
+// A CTA (8 warps) holds W_hh^T once (127 KB at H = 102) and runs 8 / WPG independent groups of R
+// sequences (WPG = warps per group = ceil(H / 64)); the groups drift apart, so one group's gate
+// phase (MUFU) overlaps another's product (FMA) on the same scheduler.  R is chosen per launch
+// (4 .. 8) so that the grid is one full wave: 4096 sequences -> 147 CTAs of 4 x 7.
+//
+// Every output's sum runs over k ascending in one FMA chain and the gate expressions are those of
+// gru_recur_kernel / gru_recur_small_kernel: the three kernels are bit-identical (tested), so the
+// kernel choice — which depends on the batch size — never changes a result.
+#pragma once
+
+#include "recur.cuh"
+#include "wg_common.cuh"
+
+namespace wg {
+
+constexpr int kRuWarps = 8;
+constexpr int kRuThreads = kRuWarps * 32;
+constexpr int kRuMaxR = 8;
+constexpr int kRuMinR = 4;
+
+__host__ __device__ inline int recur_u_hp2(int H) { return round_up(H, 2); }
+// warps per group: a lane owns one unit pair
+__host__ __device__ inline int recur_u_wpg(int H) { return recur_u_hp2(H) / 2 <= 32 ? 1 : 2; }
+__host__ __device__ inline bool recur_u_applies(int H) { return recur_u_hp2(H) / 2 <= 64; }
+// h rows: KP floats, padded so that consecutive rows start in different 16-byte bank groups
+__host__ __device__ inline int recur_u_hs_stride(int KP) { return ((KP / 4) & 1) ? KP : KP + 4; }
+__host__ __device__ inline size_t recur_u_smem_floats(int H, int R) {
+    const int KP = round_up(H, 4), HP2 = recur_u_hp2(H), WPG = recur_u_wpg(H), NGRP = kRuWarps / WPG;
+    size_t n = (size_t)KP * 3 * HP2;                          // W_hh^T as [k][gate][unit]
+    n += 2 * (size_t)NGRP * R * recur_u_hs_stride(KP);        // h, double buffered
+    n += (size_t)NGRP * 3 * R * WPG * 32 * 2;                 // gi slots (float2 per thread, gate, row)
+    n += (size_t)HP2;                                         // b_hn
+    return n;
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <int R>
+struct RuFrag {
+    float4 h[R];      // h[i] = hs[row i][k .. k+3]
+    float2 w[4][3];   // w[kk][g] = W_g[k + kk][2p .. 2p+1]
+};
+
+// GI  [B*T][ldg]   gi with b_ih (+ b_hh for r, z) folded in, column g*H + j
+// Whu [KP][3][HP2] W_hh^T, Whu[k][g][j] = w_hh[g*H + j][k], zero padded
+// out [B][T][H];   gsave (SAVE): [B*T][ldsave] = [r | z | n | W_hn h + b_hn]
+template <int R, int WPG, bool SAVE>
+__global__ void __launch_bounds__(kRuThreads, 1)
+    gru_recur_unit_kernel(const float* __restrict__ GI, const float* __restrict__ Whu, const float* __restrict__ bhn,
+                          float* __restrict__ out, long long B, int T, int H, int ldg,
+                          float* __restrict__ gsave, int ldsave) {
+    constexpr int NGRP = kRuWarps / WPG;   // groups per CTA
+    constexpr int NG = WPG * 32;           // threads per group
+    extern __shared__ __align__(16) float smem[];
+    const int KP = round_up(H, 4), HP2 = recur_u_hp2(H), NS = HP2 >> 1;
+    const int RS = recur_u_hs_stride(KP);
+    float* Ws = smem;                                        // [KP][3][HP2]
+    float* hs = Ws + (size_t)KP * 3 * HP2;                   // [2][NGRP * R][RS]
+    float2* gis = reinterpret_cast<float2*>(hs + 2 * (size_t)NGRP * R * RS);   // [NGRP][3 * R][NG]
+    float* bns = reinterpret_cast<float*>(gis + (size_t)NGRP * 3 * R * NG);    // [HP2]
+
+    const int tid = threadIdx.x;
+    const int grp = tid / NG;
+    const int p = tid - grp * NG;          // unit pair of this thread
+    const bool active = p < NS;
+    const int pc = active ? p : NS - 1;    // clamped: idle lanes load valid addresses and store nothing
+    const int j0 = 2 * pc;
+    const bool has1 = j0 + 1 < H;          // the pair's second unit exists (H odd: not in the last slot)
+    const long long b0 = (long long)blockIdx.x * (NGRP * R) + grp * R;   // first sequence of the group
+    const int H2 = 2 * H;
+
+    {
+        const int n4 = KP * 3 * HP2 / 4;   // KP % 4 == 0
+        const float4* src = reinterpret_cast<const float4*>(Whu);
+        float4* dst = reinterpret_cast<float4*>(Ws);
+        for (int e = tid; e < n4; e += kRuThreads) dst[e] = __ldg(src + e);
+    }
+    for (int e = tid; e < 2 * NGRP * R * RS; e += kRuThreads) hs[e] = 0.0f;
+    for (int e = tid; e < NGRP * 3 * R * NG; e += kRuThreads) gis[e] = make_float2(0.0f, 0.0f);
+    for (int e = tid; e < HP2; e += kRuThreads) bns[e] = e < H ? __ldg(bhn + e) : 0.0f;
+
+    // this thread's gi slots: gis[grp][g * R + i][p]; 8-byte copies where the source is 8-byte aligned
+    float2* myslots = gis + ((size_t)grp * 3 * R) * NG + p;
+    const bool gi_vec = (reinterpret_cast<uintptr_t>(GI) & 7) == 0 && (ldg & 1) == 0;
+    auto prefetch_gi = [&](int t) {
+        if (active) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const int col = g * H + j0;
+                const bool v8 = gi_vec && has1 && ((col & 1) == 0);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    if (b0 + i < B) {
+                        const float* src = GI + ((size_t)(b0 + i) * T + t) * ldg + col;
+                        float2* dst = myslots + (g * R + i) * NG;
+                        if (v8) {
+                            cp_async8(dst, src);
+                        } else {
+                            cp_async4(&dst->x, src);
+                            if (has1) cp_async4(&dst->y, src + 1);
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    __syncthreads();   // zero fills are done before any async copy may land
+    prefetch_gi(0);
+
+    float2 hprev[R];   // h_{t-1} of this thread's items
+#pragma unroll
+    for (int i = 0; i < R; ++i) hprev[i] = make_float2(0.0f, 0.0f);
+    const float2 bn = make_float2(bns[j0], has1 ? bns[j0 + 1] : 0.0f);
+    const float* wbase = Ws + j0;
+    const bool out_vec = (reinterpret_cast<uintptr_t>(out) & 7) == 0 && (H & 1) == 0;
+    const bool save_vec = SAVE && (reinterpret_cast<uintptr_t>(gsave) & 7) == 0 && (ldsave & 1) == 0 && (H & 1) == 0;
+
+    for (int t = 0; t < T; ++t) {
+        const float* hcur = hs + ((size_t)(t & 1) * NGRP + grp) * R * RS;          // h_{t-1}: read
+        float* hnxt = hs + ((size_t)((t + 1) & 1) * NGRP + grp) * R * RS;          // h_t: written
+        // ================= product: acc[i][g] = sum_k h[i][k] * W_g[k][2p, 2p+1] =================
+        float2 acc[R][3];
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+            for (int g = 0; g < 3; ++g) acc[i][g] = make_float2(0.0f, 0.0f);
+        if (t > 0) {   // h_{-1} = 0: the product is zero at t == 0
+            const float* hp = hcur;
+            const float* wp = wbase;
+            const int wk = 3 * HP2;   // floats per k
+            auto load_frag = [&](RuFrag<R>& f) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) f.h[i] = *reinterpret_cast<const float4*>(hp + i * RS);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int g = 0; g < 3; ++g)
+                        f.w[kk][g] = *reinterpret_cast<const float2*>(wp + kk * wk + g * HP2);
+                hp += 4;
+                wp += 4 * wk;
+            };
+            auto mma_frag = [&](const RuFrag<R>& f) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const float hv = kk == 0 ? f.h[i].x : kk == 1 ? f.h[i].y : kk == 2 ? f.h[i].z : f.h[i].w;
+                        const float2 hh = make_float2(hv, hv);   // FFMA2 broadcasts a scalar operand
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) acc[i][g] = __ffma2_rn(hh, f.w[kk][g], acc[i][g]);
+                    }
+                }
+            };
+            // software pipeline over KP / 4 fragments, two register buffers
+            RuFrag<R> fa, fb;
+            load_frag(fa);
+            int k4 = 4;
+#pragma unroll 1
+            for (; k4 + 4 < KP; k4 += 8) {
+                load_frag(fb);
+                mma_frag(fa);
+                load_frag(fa);
+                mma_frag(fb);
+            }
+            if (k4 < KP) {   // even number of fragments: one more pair
+                load_frag(fb);
+                mma_frag(fa);
+                mma_frag(fb);
+            } else {
+                mma_frag(fa);
+            }
+        }
+        // ================= gates, straight from the accumulators =================
+        cp_async_wait<0>();   // this thread's gi(t) slots have landed
+        float2 gi[3][R];
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int i = 0; i < R; ++i) gi[g][i] = myslots[(g * R + i) * NG];
+        if (t + 1 < T) prefetch_gi(t + 1);   // the slots are free again; lands during the next product
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            float2 hn, r, z, n, hnew;
+            // the same expressions, in the same order, as the merge + gate phases of gru_recur_kernel
+            r.x = sigmoid_f(gi[0][i].x + acc[i][0].x);
+            r.y = sigmoid_f(gi[0][i].y + acc[i][0].y);
+            z.x = sigmoid_f(gi[1][i].x + acc[i][1].x);
+            z.y = sigmoid_f(gi[1][i].y + acc[i][1].y);
+            hn.x = acc[i][2].x + bn.x;
+            hn.y = acc[i][2].y + bn.y;
+            n.x = tanh_f(gi[2][i].x + r.x * hn.x);
+            n.y = tanh_f(gi[2][i].y + r.y * hn.y);
+            hnew.x = (hprev[i].x - n.x) * z.x + n.x;
+            hnew.y = has1 ? (hprev[i].y - n.y) * z.y + n.y : 0.0f;
+            hprev[i] = hnew;
+            if (active) {
+                *reinterpret_cast<float2*>(hnxt + i * RS + j0) = hnew;
+                if (b0 + i < B) {
+                    float* op = out + ((size_t)(b0 + i) * T + t) * H + j0;
+                    if (out_vec) {
+                        *reinterpret_cast<float2*>(op) = hnew;
+                    } else {
+                        op[0] = hnew.x;
+                        if (has1) op[1] = hnew.y;
+                    }
+                    if (SAVE) {
+                        float* gs = gsave + ((size_t)(b0 + i) * T + t) * ldsave + j0;
+                        if (save_vec) {
+                            *reinterpret_cast<float2*>(gs) = r;
+                            *reinterpret_cast<float2*>(gs + H) = z;
+                            *reinterpret_cast<float2*>(gs + H2) = n;
+                            *reinterpret_cast<float2*>(gs + H2 + H) = hn;
+                        } else {
+                            gs[0] = r.x; gs[H] = z.x; gs[H2] = n.x; gs[H2 + H] = hn.x;
+                            if (has1) { gs[1] = r.y; gs[H + 1] = z.y; gs[H2 + 1] = n.y; gs[H2 + H + 1] = hn.y; }
+                        }
+                    }
+                }
+            }
+        }
+        // h_t complete for the group before anyone reads it; the buffer written at step t+1 is the one
+        // read at step t, which every warp of the group has finished with once it arrives here
+        group_barrier(1 + grp, NG);
+    }
+}
+
+}  // namespace wg

@@ -10,6 +10,10 @@ namespace wg {
 __host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// compile-time integer passed as a value (generic lambdas)
+template <int N>
+struct IntC { static constexpr int value = N; };
+
 constexpr int kNumSMs = 148;        // B200: 2 dies x 74 SMs
 constexpr int kMaxSmemOptin = 232448;  // 227 KB usable per CTA
 
