@@ -566,7 +566,7 @@ def main():
             if fn_b is None:
                 gpu_eager = {"unavailable": "oracle/_ref not built (the reference classes are needed on the GPU)"}
             else:
-                with torch.no_grad():
+                def eager_batched():
                     for _ in range(2):
                         ye = fn_b(adj, x)
                     torch.cuda.synchronize(dev)
@@ -577,23 +577,39 @@ def main():
                         ye = fn_b(adj, x)
                     g1.record()
                     torch.cuda.synchronize(dev)
-                    ms_e = g0.elapsed_time(g1) / reps_e
-                    err_e = float((ye - y).abs().max() / ye.abs().max())
-                    del ye
+                    return g0.elapsed_time(g1) / reps_e, float((ye - y).abs().max() / ye.abs().max())
+
+                with torch.no_grad():
+                    # PyTorch's defaults, i.e. what `python src/main.py` gets on this GPU: fp32 matmuls, but the
+                    # cuDNN GRU is allowed TF32 (torch.backends.cudnn.allow_tf32 defaults to True)
+                    ms_d, err_d = eager_batched()
                     for _ in range(3):
                         fn_w(adj, x[:4])
                     torch.cuda.synchronize(dev)
+                    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     g0.record()
                     fn_w(adj, x[:64])
                     g1.record()
                     torch.cuda.synchronize(dev)
                     ms_w = g0.elapsed_time(g1) / 64
+                    # strict fp32 (the precision this library's FP32 path is held to)
+                    prev = torch.backends.cudnn.allow_tf32
+                    torch.backends.cudnn.allow_tf32 = False
+                    try:
+                        ms_e, err_e = eager_batched()
+                    finally:
+                        torch.backends.cudnn.allow_tf32 = prev
                 gpu_eager = {"kind": kind, "value": Bg / (ms_e * 1e-3), "unit": UNIT, "ms_per_pass": ms_e,
-                             "batch": Bg, "as_written_ms_per_window": ms_w,
-                             "ours_vs_eager_normalised_max_diff": err_e,
+                             "batch": Bg, "ours_vs_eager_normalised_max_diff": err_e,
+                             "pytorch_defaults": {"value": Bg / (ms_d * 1e-3), "ms_per_pass": ms_d,
+                                                  "ours_vs_eager_normalised_max_diff": err_d,
+                                                  "note": "torch.backends.cudnn.allow_tf32 = True (default): the cuDNN GRU "
+                                                          "may use TF32"},
+                             "as_written_ms_per_window": ms_w,
                              "what": "the reference's GraphConvLayer / nn.GRU modules (oracle/_ref, unmodified) in PyTorch "
-                                     "eager on this GPU, fp32 (TF32 off): batched through its sub-modules at the bench "
-                                     "batch, and as written — one model(adj_matrix, batch_x) call per window (main.py:101-102)"}
+                                     "eager on this GPU (cuBLAS + cuDNN GRU), strict fp32 (cudnn.allow_tf32 = False): batched "
+                                     "through its sub-modules at the bench batch; `as_written` = one model(adj_matrix, batch_x) "
+                                     "call per window (main.py:101-102) with PyTorch's defaults"}
             torch.cuda.empty_cache()
         except Exception as e:  # the comparator must never take the bench line down
             gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:300]}

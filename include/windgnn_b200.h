@@ -192,7 +192,8 @@ int wg_denorm_last_step_f32(const float* out, float* pred, int64_t B, int T, int
  *   loss = nn.MSELoss()(outputs, batch_y)  (:49,:72) -> wg_mse_loss_grad_f32 (loss and dL/d outputs)
  *   loss.backward()                        (:76)     -> wg_gcn_gru_backward_f32
  *   optimizer.step()  (torch.optim.Adam, :52,:77)    -> wg_adam_step_f32
- * FP32 throughout, dense adjacency, F_in / F_hid / F_out <= 16, H <= 106 (W_hh resident in shared
+ * FP32 throughout, dense adjacency, F_in / F_hid / F_out <= 16, H <= 106 (the limit the
+ * planner enforces: W_hh and the recurrent state resident in shared
  * memory; the shipped models).
  *
  * The forward is the inference path's three kernels; the recurrence additionally saves the gate

@@ -107,3 +107,36 @@ def test_training_planning_and_validation():
     assert lib.wg_mse_loss_grad_f32(None, None, 0, None, None, None, 0, 0, None) == _lib.WG_ERR_BAD_ARG
     assert lib.wg_adam_step_f32(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, 0, None) == _lib.WG_ERR_BAD_ARG
     assert lib.wg_adam_step_f32(None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, 0, None) == _lib.WG_OK
+
+
+def test_integration_doc_binding_matches_the_library():
+    """INTEGRATION.md section 3 is the binding a maintainer copies: execute it against the built library
+    and compare what it declares with the typed binding the package itself uses (ABI v3: `flags`
+    after `chunk` in both calls)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    sec = text[text.index("## 3. Raw ctypes binding"):text.index("## 4. Contract")]
+    code = re.search(r"```python\n(.*?)```", sec, flags=re.S).group(1)
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)   # the snippet opens the library by its in-tree relative path
+    try:
+        exec(compile(code, "INTEGRATION.md#3", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    doc = ns["lib"]
+    for name in ("wg_gcn_gru_workspace_bytes", "wg_gcn_gru_forward_f32"):
+        restype, argtypes = _lib._SIGNATURES[name]
+        fn = getattr(doc, name)
+        assert fn.restype is restype
+        assert [ctypes.sizeof(a) for a in fn.argtypes] == [ctypes.sizeof(a) for a in argtypes]
+        assert len(fn.argtypes) == len(argtypes)
+    dims34 = (168, 34, 13, 13, 13, 102)
+    # the documented call and the package's typed call plan the same workspace, for both flag values
+    for flags in (0, ns["WG_FLAG_TENSOR_CORES"]):
+        assert doc.wg_gcn_gru_workspace_bytes(4096, *dims34, 0, flags) == \
+            _lib.load().wg_gcn_gru_workspace_bytes(4096, *dims34, 0, flags) > 0
+    # argument validation through the documented signature: a short workspace is rejected as such
+    fake = ctypes.c_void_p(256)
+    rc = doc.wg_gcn_gru_forward_f32(*([fake] * 11), 2, *dims34, 0, 0, fake, 16, 0, None)
+    assert rc == _lib.WG_ERR_WORKSPACE and b"too small" in doc.wg_last_error()
+    assert callable(ns["gcn_gru_forward"])

@@ -61,3 +61,32 @@ def test_mercator_matches_oracle_bitwise():
 
     ll = station_latlon(34)
     assert np.array_equal(windgnn_b200.mercator(ll), oracle_mercator(ll))
+
+
+def test_gradients_wrt_data_are_refused_up_front():
+    """The reference never differentiates w.r.t. its data (main.py:66-77) and the library has no such
+    gradient: asking for one fails immediately instead of silently returning None."""
+    model = windgnn_b200.GCN_GRU(13, 13, 13, 91, 21)
+    with pytest.raises(RuntimeError, match="attr_matrix / adj_matrix"):
+        model(torch.eye(7), torch.zeros(1, 4, 7, 13, requires_grad=True))
+
+
+@pytest.mark.gpu
+def test_untrainable_paths_run_forward_and_explain_at_backward():
+    """The reference module trains at any size; here training exists for dense graphs with <= 128 stations and
+    GCN widths <= 16.  Elsewhere the forward still works under grad mode (as main.py:66 calls it) and
+    backward() fails with the reason instead of 'autograd not implemented'."""
+    dev = "cuda:0"
+    layer = windgnn_b200.GraphConvLayer(13, 13).to(dev)
+    out = layer(torch.eye(7, device=dev), torch.rand(4, 7, 13, device=dev))
+    assert out.requires_grad and out.shape == (4, 7, 13)
+    with pytest.raises(RuntimeError, match="no autograd formula"):
+        out.sum().backward()
+    wide = windgnn_b200.GCN_GRU(13, 32, 13, 13 * 7, 21).to(dev)   # hidden width 32: the CSR path
+    y = wide(torch.eye(7, device=dev), torch.rand(2, 4, 7, 13, device=dev))
+    assert y.shape == (2, 4, 21)
+    with pytest.raises(RuntimeError, match="training is implemented for dense graphs"):
+        y.sum().backward()
+    with torch.no_grad():
+        y2 = wide(torch.eye(7, device=dev), torch.rand(2, 4, 7, 13, device=dev))
+    assert not y2.requires_grad

@@ -174,3 +174,35 @@ def test_train_oracle_adam_trajectory_matches_reference():
     np.testing.assert_allclose(losses, g["losses3"], rtol=1e-9)
     for k in PARAM_KEYS:
         np.testing.assert_allclose(P[k], g["param3__" + k.replace(".", "__")], atol=1e-7)
+
+
+def test_reference_copy_reproduces_the_goldens_bit_for_bit():
+    """oracle/_ref (git-ignored, built by oracle/build_ref.py from /root/reference) holds the unmodified
+    reference modules that bench.py's reference / cpu_baseline / gpu_eager legs run."""
+    import os
+
+    import pytest
+    import torch
+
+    from conftest import ROOT, golden, load_checkpoint
+    from oracle.ref_loader import (reference_classes, reference_forward_as_written, reference_forward_batched,
+                                   reference_model)
+
+    if reference_classes() is None:
+        from oracle.build_ref import build_ref
+
+        if not build_ref():
+            pytest.skip("no /root/reference here and oracle/_ref not built")
+    import json
+
+    man = json.load(open(os.path.join(ROOT, "oracle", "_ref", "MANIFEST.json")))
+    assert sorted(man["files"]) == ["step5_gcn_layer_model.py", "step6_gcn_gru_combined_model.py"]
+    for S in (7, 34):
+        g = golden(f"fwd_{S}.npz")
+        adj = torch.from_numpy(golden(f"adj_ref_{S}.npy").astype(np.float32))
+        model = reference_model(load_checkpoint(S), (13, 13, 13, 13 * S, 3 * S))
+        x = torch.from_numpy(g["x"])
+        y = reference_forward_as_written(model, adj, x)
+        assert np.array_equal(y.numpy(), g["y_ref_f32"])        # the very code that made the goldens
+        yb = reference_forward_batched(model, adj, x)
+        assert normalised_max_error(yb.numpy(), g["y_ref_f32"]) < 3e-6

@@ -84,7 +84,10 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    # the unmodified reference modules when oracle/_ref has been built (oracle/build_ref.py), else the port
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "step6_gcn_gru_combined_model.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["same_config"] is False   # 16 of 4096 here
 
 
 # ---- data-parallel training: one flat gradient bucket, one all-reduce, mean folded into the optimiser ----
@@ -141,3 +144,18 @@ def test_allreduce_mean_is_identity_without_a_process_group():
     assert allreduce_mean_(t) == 1.0 and t.tolist() == [0, 1, 2, 3, 4]
     with pytest.raises(RuntimeError):
         split_flat(t, [(2,), (2,)])
+
+
+def test_uneven_shards_weighting_reproduces_the_global_mean():
+    from windgnn_b200.train import shard_weight
+
+    assert shard_weight(512, 512) == 1.0                        # single process
+    # two ranks with 3 and 5 windows: mean of the weighted local means == the global mean
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    a, b = rng.random(3), rng.random(5)
+    w_a, w_b = 3 * 2 / 8, 5 * 2 / 8                             # what shard_weight returns under world = 2
+    assert (w_a * a.mean() + w_b * b.mean()) / 2 == pytest.approx(np.concatenate([a, b]).mean())
+    with pytest.raises(ValueError):
+        shard_weight(4, 0)

@@ -70,8 +70,13 @@ def test_windows_full_size_properties():
     # a permutation only reorders windows
     x2, y2 = windgnn_b200.create_sequences(table)
     assert torch.equal(x2[perm], x) and torch.equal(y2[perm], y)
-    with pytest.raises(_lib.WindGNNError):
+    with pytest.raises(RuntimeError, match="complete windows"):
         windgnn_b200.create_sequences(table[: 168 * 3 + 2], perm=torch.arange(3, device=DEV))
+    # a SHORT perm naming a window that does not exist (or a negative one) must not read out of bounds
+    with pytest.raises(RuntimeError, match="complete windows"):
+        windgnn_b200.create_sequences(table, perm=torch.tensor([N], device=DEV))
+    with pytest.raises(RuntimeError, match="complete windows"):
+        windgnn_b200.create_sequences(table, perm=torch.tensor([0, -1], device=DEV))
 
 
 @pytest.mark.gpu

@@ -11,7 +11,8 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libwindgnn_b200.so")
+# WINDGNN_B200_LIB: an experiment build of the same library (windgnn_b200/build.py, WG_LIB_SUFFIX)
+LIB_PATH = os.environ.get("WINDGNN_B200_LIB") or os.path.join(HERE, "lib", "libwindgnn_b200.so")
 
 WG_OK = 0
 WG_ERR_BAD_ARG = -1

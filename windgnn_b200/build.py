@@ -19,6 +19,12 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libwindgnn_b200.so")
+# experiment builds (WG_NVCC_FLAGS=-D...) go to their own file so that they never replace the product:
+# WG_LIB_SUFFIX=trace -> lib/libwindgnn_b200_trace.so, loaded with WINDGNN_B200_LIB=<that path>
+_SUFFIX = os.environ.get("WG_LIB_SUFFIX", "")
+if _SUFFIX:
+    LIB = os.path.join(LIBDIR, f"libwindgnn_b200_{_SUFFIX}.so")
+    BUILD = os.path.join(HERE, f"build_{_SUFFIX}")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]

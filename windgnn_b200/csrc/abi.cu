@@ -1179,6 +1179,10 @@ int wg_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp
 
 #ifdef WG_RC_TRACE
 // debug build only (not declared in the public header)
+int wg_debug_read_unit_trace(long long* host, int n) {
+    if (n > 8 * 256 * 5) n = 8 * 256 * 5;
+    return (int)cudaMemcpyFromSymbol(host, wg::g_ru_trace, sizeof(long long) * n);
+}
 int wg_debug_read_trace(long long* host, int n) {
     if (n > 2 * 8 * 256) n = 2 * 8 * 256;
     return (int)cudaMemcpyFromSymbol(host, wg::g_rc_trace, sizeof(long long) * n);

@@ -56,6 +56,17 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 
+#ifdef WG_RC_TRACE
+// debug build only: clock stamps of CTA 0, per warp and step (5 stamps per step)
+__device__ long long g_ru_trace[8 * 256 * 5];
+#define WG_RU_TRACE(slot)                                                                                   \
+    do {                                                                                                    \
+        if (blockIdx.x == 0 && (tid & 31) == 0 && t < 256) g_ru_trace[((tid >> 5) * 256 + t) * 5 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define WG_RU_TRACE(slot) do { } while (0)
+#endif
+
 template <int R>
 struct RuFrag {
     float4 h[R];      // h[i] = hs[row i][k .. k+3]
@@ -141,6 +152,7 @@ __global__ void __launch_bounds__(kRuThreads, 1)
     for (int t = 0; t < T; ++t) {
         const float* hcur = hs + ((size_t)(t & 1) * NGRP + grp) * R * RS;          // h_{t-1}: read
         float* hnxt = hs + ((size_t)((t + 1) & 1) * NGRP + grp) * R * RS;          // h_t: written
+        WG_RU_TRACE(0);
         // ================= product: acc[i][g] = sum_k h[i][k] * W_g[k][2p, 2p+1] =================
         float2 acc[R][3];
 #pragma unroll
@@ -193,6 +205,7 @@ __global__ void __launch_bounds__(kRuThreads, 1)
                 mma_frag(fa);
             }
         }
+        WG_RU_TRACE(1);
         // ================= gates, straight from the accumulators =================
         cp_async_wait<0>();   // this thread's gi(t) slots have landed
         float2 gi[3][R];
@@ -201,6 +214,7 @@ __global__ void __launch_bounds__(kRuThreads, 1)
 #pragma unroll
             for (int i = 0; i < R; ++i) gi[g][i] = myslots[(g * R + i) * NG];
         if (t + 1 < T) prefetch_gi(t + 1);   // the slots are free again; lands during the next product
+        WG_RU_TRACE(2);
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             float2 hn, r, z, n, hnew;
@@ -243,7 +257,9 @@ __global__ void __launch_bounds__(kRuThreads, 1)
         }
         // h_t complete for the group before anyone reads it; the buffer written at step t+1 is the one
         // read at step t, which every warp of the group has finished with once it arrives here
+        WG_RU_TRACE(3);
         group_barrier(1 + grp, NG);
+        WG_RU_TRACE(4);
     }
 }
 

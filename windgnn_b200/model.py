@@ -16,6 +16,20 @@ import torch.nn as nn
 from . import ops
 
 
+class _InferenceOnly(torch.autograd.Function):
+    """Forward of a path that has no backward in the library: the result still takes part in autograd (so a
+    forward under grad mode behaves like the reference's), and backward() raises with the reason."""
+
+    @staticmethod
+    def forward(ctx, message, fn, *params):
+        ctx.message = message
+        return fn()
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise RuntimeError(ctx.message)
+
+
 class GraphConvLayer(nn.Module):
     """``relu((adj @ attr) @ weight + bias)`` — step5:13-23.  Init as step5:8-10."""
 
@@ -25,6 +39,16 @@ class GraphConvLayer(nn.Module):
         self.bias = nn.Parameter(torch.zeros(output_dim))
 
     def forward(self, adj_matrix, attr_matrix):
+        if torch.is_grad_enabled() and any(
+                t.requires_grad for t in (self.weight, self.bias, attr_matrix, adj_matrix)):
+            # the stand-alone layer op has no backward (training goes through GCN_GRU, train.py): the forward
+            # still works under grad mode, and a later backward() says why it cannot
+            return _InferenceOnly.apply(
+                "windgnn_b200.GraphConvLayer has no autograd formula: train through windgnn_b200.GCN_GRU, whose "
+                "forward records the library backward, or call the layer under torch.no_grad()",
+                lambda: ops.gcn_layer(adj_matrix.detach(), attr_matrix.detach(), self.weight.detach(),
+                                      self.bias.detach()),
+                self.weight, self.bias)
         return ops.gcn_layer(adj_matrix, attr_matrix, self.weight, self.bias)
 
 
@@ -63,13 +87,26 @@ class GCN_GRU(nn.Module):
             self.gru.weight_ih_l0, self.gru.weight_hh_l0, self.gru.bias_ih_l0, self.gru.bias_hh_l0,
         )
         widths = (self.conv1.weight.shape[0], self.conv1.weight.shape[1], self.conv2.weight.shape[1])
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if torch.is_grad_enabled() and (attr_matrix.requires_grad or adj_matrix.requires_grad):
+            # the reference never differentiates w.r.t. its data (main.py:66-77); the library has no such gradient
+            raise RuntimeError("windgnn_b200.GCN_GRU: gradients w.r.t. attr_matrix / adj_matrix are not implemented")
         if adj_matrix.shape[0] > self.DENSE_MAX_STATIONS or max(widths) > 16:
-            # scaled shapes (thousands of stations, wide hidden layer): CSR adjacency path
             key = (adj_matrix.data_ptr(), adj_matrix._version, tuple(adj_matrix.shape))
             if self._csr_cache is None or self._csr_cache[0] != key:
                 self._csr_cache = (key, ops.dense_to_csr(adj_matrix))
-            out = ops.gcn_gru_forward_csr(*self._csr_cache[1], attr_matrix, *params, self.chunk)
-        elif torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            if needs_grad:
+                # forward works under grad mode (main.py:66 style calls); backward() explains the limit
+                out = _InferenceOnly.apply(
+                    "windgnn_b200.GCN_GRU: training is implemented for dense graphs with at most "
+                    f"{self.DENSE_MAX_STATIONS} stations and GCN widths <= 16 (got {adj_matrix.shape[0]} stations, "
+                    f"widths {widths}); the scaled shapes are inference-only",
+                    lambda: ops.gcn_gru_forward_csr(*self._csr_cache[1], attr_matrix, *[p.detach() for p in params],
+                                                    self.chunk),
+                    *params)
+            else:
+                out = ops.gcn_gru_forward_csr(*self._csr_cache[1], attr_matrix, *params, self.chunk)
+        elif needs_grad:
             # training (main.py:66 runs with grad enabled): forward that saves the gate values, library
             # backward (train.py); FP32 path only
             from .train import GcnGruFunction

@@ -10,22 +10,29 @@ and supplies the current stream; all arithmetic happens in ``libwindgnn_b200.so`
 
 from __future__ import annotations
 
+import threading
 from typing import Dict, Tuple
 
 import torch
 
 from . import _lib
 
-_WORKSPACES: Dict[Tuple[int, str], torch.Tensor] = {}
+_WORKSPACES: Dict[Tuple[int, int, str], torch.Tensor] = {}
+_WS_LOCK = threading.Lock()
 
 
 def _workspace(device: torch.device, nbytes: int, tag: str = "fwd") -> torch.Tensor:
-    """Per-device scratch, grown on demand and reused (stream-ordered use only)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-        _WORKSPACES[key] = ws
+    """Scratch per (device, CUDA stream, tag), grown on demand and reused.  The library calls are
+    stream-ordered and keep no pointer after they return, so calls on ONE stream may share a buffer;
+    calls on different streams (or from different threads, which have different current streams or
+    serialise on the lock while looking the buffer up) get different buffers."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(device).cuda_stream, tag)
+    with _WS_LOCK:
+        ws = _WORKSPACES.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+            _WORKSPACES[key] = ws
     return ws
 
 

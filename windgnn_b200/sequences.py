@@ -49,6 +49,12 @@ def create_sequences(table: torch.Tensor, seq_length: int = SEQ_LENGTH, perm: to
             raise RuntimeError("perm must be a CUDA int64 tensor")
         perm = perm.contiguous()
         N = perm.numel()
+        # every entry must name a complete window (the kernels index table[perm[n] * L ...] directly)
+        n_valid = int(lib.wg_num_windows(Ttot, seq_length, horizons))
+        if N and (int(perm.min()) < 0 or int(perm.max()) >= n_valid):
+            raise RuntimeError(
+                f"perm entries must lie in [0, {n_valid}) — the table holds {n_valid} complete windows of "
+                f"{seq_length} rows with {horizons} label rows after them; got [{int(perm.min())}, {int(perm.max())}]")
     y = torch.empty((N, seq_length, horizons * S), dtype=torch.float32, device=dev)
     if perm is None and want_x:
         x = table[: N * seq_length].view(N, seq_length, S, F)  # zero-copy: windows are contiguous

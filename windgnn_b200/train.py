@@ -153,6 +153,17 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> float:
     return 1.0 / world
 
 
+def shard_weight(local_batch: int, global_batch: int, group=None) -> float:
+    """Weight of a rank's local-mean gradient in the average over ranks that reproduces the global mean:
+    ``local_batch * world / global_batch`` (1 for equal shards or a single process)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if global_batch <= 0:
+        raise ValueError("global_batch must be positive")
+    return float(local_batch) * world / float(global_batch)
+
+
 class Trainer:
     """Fused data-parallel training step for a ``windgnn_b200.GCN_GRU`` on one GPU per process.
 
@@ -186,14 +197,23 @@ class Trainer:
         self.exp_avg_sq = torch.zeros_like(self.flat)
 
     @torch.no_grad()
-    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    def step(self, x: torch.Tensor, y: torch.Tensor, global_batch: Optional[int] = None) -> torch.Tensor:
         """One optimisation step on this rank's shard ``x [B,T,S,F]``, ``y [B,T,H]``.  Returns the
-        local loss (device scalar; no host synchronisation)."""
+        local loss (device scalar; no host synchronisation).
+
+        The ranks' gradients of their LOCAL mean losses are averaged, which is the gradient of the global
+        mean-squared error when every rank holds the same number of windows.  For uneven shards pass
+        ``global_batch`` (the number of windows over all ranks): this rank's upstream gradient is then
+        weighted by ``B_local * world / global_batch`` so that the average is the global gradient."""
         lib = _lib.load()
         dev = self.flat.device
         ps = [p.data for p in self.params]
         out, ws = forward_train(self.adj, x, ps)
         loss, d_out = mse_loss_grad(out, y)
+        if global_batch is not None:
+            w = shard_weight(x.shape[0], global_batch, self.group)
+            if w != 1.0:
+                d_out.mul_(w)
         backward(self.adj, x, ps, out, d_out, ws, self.grads)
         scale = allreduce_mean_(self.grads, self.group)
         self.step_count += 1
