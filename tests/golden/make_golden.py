@@ -17,6 +17,10 @@ What it writes (all small, all committed):
 ``fwd_34_short.npz``     same, T = 1 and T = 5 windows
 ``fwd_rand.npz``         a randomly initialised ``GCN_GRU(6, 10, 13, 65, 11)`` on S = 5
                          (exercises F_in != F_hid != 13 and H != 3S), with its parameters
+``fwd_wide.npz``         the reference CLASS at the scaled shape's widths, ``GCN_GRU(13, 128, 13, 13*300, 128)`` on a
+                         300-station kNN(8) graph (dense matrix, as the reference takes it), B = 2, T = 6, with its
+                         parameters: pins the CSR path, which re-associates layer 2 as ``A.(G1.W2)``
+                         (``python tests/golden/make_golden.py --only-wide`` writes just this file)
 ``manifest.json``        sha256 of every file + library versions
 """
 
@@ -73,8 +77,53 @@ def make_windows_golden():
     np.savez_compressed(os.path.join(HERE, "windows.npz"), table=table, x=x, y=y, indices=idx, seq_length=L)
 
 
+def make_wide_golden():
+    """``fwd_wide.npz``: the unmodified reference class at wide dims (hidden 128, GRU hidden 128) on a
+    300-station kNN graph.  The graph comes from the oracle's kNN generator (the reference has none);
+    the forward is the reference's own ``model(adj, x[b:b+1])``, in fp32 and in fp64."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import knn_graph_f64, synthetic_coordinates
+
+    S, Fh, H, T, B = 300, 128, 128, 6, 2
+    adj64 = knn_graph_f64(synthetic_coordinates(S, seed=3), k=8)
+    adj = torch.tensor(adj64).float()
+    torch.manual_seed(11)
+    model = GCN_GRU(13, Fh, 13, 13 * S, H).eval()
+    with torch.no_grad():
+        model.conv1.weight.mul_(0.05)       # SURVEY.md 8(d): unscaled randn saturates the GRU at this width
+        model.conv2.weight.mul_(0.05)
+        model.conv1.bias.uniform_(-0.1, 0.1)
+        model.conv2.bias.uniform_(-0.1, 0.1)
+    x = torch.rand(B, T, S, 13, generator=torch.Generator().manual_seed(12))
+    y32 = ref_forward(model, adj, x)
+    m64 = GCN_GRU(13, Fh, 13, 13 * S, H).double()
+    m64.load_state_dict(model.state_dict())
+    y64 = ref_forward(m64, adj.double(), x.double())
+    np.savez_compressed(
+        os.path.join(HERE, "fwd_wide.npz"), adj=adj.numpy(), x=x.numpy(), y_ref_f32=y32.numpy(), y_ref_f64=y64.numpy(),
+        **{k.replace(".", "__"): v.numpy() for k, v in model.state_dict().items()})
+    print("fwd_wide.npz: out", tuple(y32.shape), "fp32 vs fp64 normalised max",
+          float(np.abs(y32.numpy() - y64.numpy()).max() / np.abs(y64.numpy()).max()))
+
+
+def update_manifest_entry(fn):
+    path = os.path.join(HERE, "manifest.json")
+    with open(path) as f:
+        manifest = json.load(f)
+    with open(os.path.join(HERE, fn), "rb") as f:
+        manifest["sha256"][fn] = hashlib.sha256(f.read()).hexdigest()
+    with open(path, "w") as f:
+        json.dump(manifest, f, indent=1)
+
+
 def main():
+    if "--only-wide" in sys.argv:
+        torch.set_num_threads(1)
+        make_wide_golden()
+        update_manifest_entry("fwd_wide.npz")
+        return
     make_windows_golden()
+    make_wide_golden()
     torch.manual_seed(0)
     np.random.seed(0)
     torch.set_num_threads(1)  # deterministic summation order in MKL

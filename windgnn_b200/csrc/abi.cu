@@ -16,7 +16,9 @@
 #include "gru_bwd.cuh"
 #include "inproj.cuh"
 #include "inproj_tc.cuh"
+#include "inproj_tc2.cuh"
 #include "recur.cuh"
+#include "recur_tc.cuh"
 #include "recur_unit.cuh"
 #include "sgemm.cuh"
 #include "train_misc.cuh"
@@ -71,9 +73,10 @@ struct Plan {
     int NPR;       // columns of packed w_hh^T: G rounded up to 80 (one warp's column block)
     bool sparse;   // CSR graph path: adds the Z scratch of the sparse GCN kernels
     bool tc;       // tensor-core (3xTF32 tcgen05) input projection: U and w_ih kept as hi + lo
-    wg::TcShape tcs;
-    size_t off_u_lo, off_wp_lo;
+    wg::Tc2Shape tc2;
     size_t off_wp, off_bias, off_wht, off_whu, off_bhn, off_u, off_gi, off_z, total;
+    bool tc_recur;             // tensor-core recurrence (recur_tc.cuh): W_hh packed as fp16 hi + lo
+    size_t off_whh_hi, off_whh_lo;
 };
 
 long long default_chunk(long long B, size_t bytes_per_seq) {
@@ -99,35 +102,41 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     if (flags & ~WG_FLAG_TENSOR_CORES) return fail(WG_ERR_BAD_ARG, "unknown flags 0x%x", flags);
     p.I = S * Fo;
     p.G = 3 * H;
-    p.IP = wg::round_up(p.I, wg::kIpBK);
+    // tensor-core projection (inproj_tc2.cuh): only on the dense small-graph path and when two accumulators of
+    // the gate slice fit TMEM; it consumes the same fp32 U tiles, K padded to its 32-k stage
+    p.tc2 = wg::tc2_shape(p.G, p.I);
+    p.tc = (flags & WG_FLAG_TENSOR_CORES) != 0 && !sparse;
+    if (p.tc && !p.tc2.ok)
+        return fail(WG_ERR_UNSUPPORTED, "tensor-core projection: unsupported gate width 3H = %d", p.G);
+    p.IP = p.tc ? p.tc2.KP : wg::round_up(p.I, wg::kIpBK);
     p.NPB = wg::round_up(p.G, wg::kIpBN);
     p.GP = wg::round_up(p.G, 4);
     p.KP = wg::round_up(H, 4);
     p.NPR = wg::recur_np(p.G);
-    // tensor-core projection: only on the dense small-graph path and when the gate width fits TMEM
-    p.tcs = wg::tc_shape(p.G);
-    p.tc = (flags & WG_FLAG_TENSOR_CORES) != 0 && !sparse;
-    if (p.tc && !p.tcs.ok)
-        return fail(WG_ERR_UNSUPPORTED, "tensor-core projection: unsupported gate width 3H = %d", p.G);
     {
-        const size_t per_seq = (size_t)T * ((size_t)p.IP * (p.tc ? 2 : 1) + p.GP + (sparse ? (size_t)S * Fo : 0)) * 4;
+        const size_t per_seq = (size_t)T * ((size_t)p.IP + p.GP + (sparse ? (size_t)S * Fo : 0)) * 4;
         p.chunk = chunk > 0 ? chunk : default_chunk(B, per_seq);
         if (p.chunk > B && B > 0) p.chunk = B;
     }
     size_t o = 0;
-    const int wrows = p.tc ? (p.tcs.NP > p.NPB ? p.tcs.NP : p.NPB) : p.NPB;
-    p.off_wp = o;   o = align_up(o + (size_t)wrows * p.IP * 4);
-    p.off_wp_lo = o; if (p.tc) o = align_up(o + (size_t)wrows * p.IP * 4);
+    const int wrows = p.tc ? (p.tc2.NP > p.NPB ? p.tc2.NP : p.NPB) : p.NPB;
+    // packed w_ih: fp32 [N/64][K][64] for the FFMA GEMM, or fp16 hi + lo stage blocks for the tensor cores
+    p.off_wp = o;   o = align_up(o + (p.tc ? wg::tc2_w_halves(p.tc2) * 2 : (size_t)wrows * p.IP * 4));
     p.off_bias = o; o = align_up(o + (size_t)(wrows > 512 ? wrows : 512) * 4);
     p.off_wht = o;  o = align_up(o + (size_t)p.KP * p.NPR * 4);
     p.off_whu = o;  // [k][gate][unit] (recur_unit.cuh), only for hidden sizes that kernel serves
     if (wg::recur_u_applies(H)) o = align_up(o + (size_t)p.KP * 3 * wg::recur_u_hp2(H) * 4);
     p.off_bhn = o;  o = align_up(o + (size_t)p.KP * 4);
+    p.tc_recur = (flags & WG_FLAG_TENSOR_CORES) != 0 && wg::recur_tc_applies(H) &&
+                 wg::recur_tc_smem_bytes(H) <= (size_t)wg::kMaxSmemOptin;
+    p.off_whh_hi = o; if (p.tc_recur) o = align_up(o + wg::recur_tc_w_halves(H) * 2);
+    p.off_whh_lo = o; if (p.tc_recur) o = align_up(o + wg::recur_tc_w_halves(H) * 2);
     const size_t rows = (size_t)p.chunk * T;
     const size_t rows_tiled = (rows + wg::kUTileRows - 1) / wg::kUTileRows * wg::kUTileRows;
     p.off_u = o;    o = align_up(o + rows_tiled * p.IP * 4);  // K-major 128-row tiles
-    p.off_u_lo = o; if (p.tc) o = align_up(o + rows_tiled * p.IP * 4);
-    p.off_gi = o;   o = align_up(o + rows * p.GP * 4);
+    // GI: the tensor-core recurrence reads whole groups of kRtSeqs sequences (rows past the batch are scratch)
+    const size_t rows_gi = (size_t)((p.chunk + wg::kRtSeqs - 1) / wg::kRtSeqs * wg::kRtSeqs) * T;
+    p.off_gi = o;   o = align_up(o + rows_gi * p.GP * 4);
     // sparse path scratch: row-major U (rows x S*Fo) + one [Fo][S] row per resident CTA
     p.off_z = o;    if (sparse) o = align_up(o + (rows + wg::kNumSMs) * (size_t)S * Fo * 4);
     p.total = o;
@@ -149,39 +158,23 @@ T* ws_ptr(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>
 // ---------------------------------------------------------------------------------------------
 // parameter packing (tiny; runs every call so the library stays stateless)
 // ---------------------------------------------------------------------------------------------
-// tc_np > 0: w_ih goes out as TF32 hi / lo parts in the UMMA K-major layout [k / 4][tc_np][4]
+// pack_wih: 0 when the tensor path packs w_ih itself (pack_wih_tc2_kernel)
 __global__ void pack_params_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                    const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                                   float* __restrict__ wp, float* __restrict__ wp_lo, float* __restrict__ bias,
+                                   float* __restrict__ wp, float* __restrict__ bias,
                                    float* __restrict__ wht, float* __restrict__ whu, float* __restrict__ bhn, int I,
-                                   int H, int IP, int NPB, int KP, int NPR, int tc_np, int tc_ne, int n_bias) {
+                                   int H, int IP, int NPB, int KP, int NPR, int pack_wih, int n_bias) {
     const int G = 3 * H;
-    const long long n_wp = tc_np > 0 ? (long long)tc_np * IP : (long long)NPB * IP;
+    const long long n_wp = pack_wih ? (long long)NPB * IP : 0;
     const long long n_wht = (long long)KP * NPR;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (long long e = t0; e < n_wp; e += stride) {
-        if (tc_np > 0) {
-            // destination layout [n / tc_ne][k / 4][n % tc_ne][4] (one contiguous image per column slice)
-            const int j = (int)(e & 3);
-            long long r = e >> 2;
-            const int nl = (int)(r % tc_ne);
-            r /= tc_ne;
-            const int kc = (int)(r % (IP >> 2)), nt = (int)(r / (IP >> 2));
-            const int n = nt * tc_ne + nl, k = kc * 4 + j;
-            const float v = (n < G && k < I) ? w_ih[(size_t)n * I + k] : 0.0f;
-            uint32_t t;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
-            const float hi = __uint_as_float(t);
-            wp[e] = hi;
-            wp_lo[e] = v - hi;
-        } else {
-            // destination layout [n / 64][k][n % 64] (K-major 64-column tiles, see inproj.cuh)
-            const int nl = (int)(e % wg::kIpBN);
-            const long long r = e / wg::kIpBN;
-            const int k = (int)(r % IP), n = (int)(r / IP) * wg::kIpBN + nl;
-            wp[e] = (n < G && k < I) ? w_ih[(size_t)n * I + k] : 0.0f;
-        }
+        // destination layout [n / 64][k][n % 64] (K-major 64-column tiles, see inproj.cuh)
+        const int nl = (int)(e % wg::kIpBN);
+        const long long r = e / wg::kIpBN;
+        const int k = (int)(r % IP), n = (int)(r / IP) * wg::kIpBN + nl;
+        wp[e] = (n < G && k < I) ? w_ih[(size_t)n * I + k] : 0.0f;
     }
     for (long long e = t0; e < n_wht; e += stride) {
         const int k = (int)(e / NPR), n = (int)(e % NPR);
@@ -344,17 +337,16 @@ int launch_gcn_sparse(const Plan& p, void* ws, const Csr& g, const float* x, con
 }
 
 int launch_inproj_tc(const Plan& p, void* ws, long long rows, cudaStream_t st) {
-    const long long m_tiles = (rows + wg::kTcBM - 1) / wg::kTcBM;
+    const long long m_tiles = (rows + wg::kT2BM - 1) / wg::kT2BM;
     if (m_tiles < 1) return WG_OK;
-    const wg::TcShape& t = p.tcs;
-    WG_CUDA(cudaFuncSetAttribute(wg::inproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const wg::Tc2Shape& t = p.tc2;
+    WG_CUDA(cudaFuncSetAttribute(wg::inproj_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)t.smem_bytes));
     const long long tiles = m_tiles * t.n_nt;
     const unsigned grid = (unsigned)(tiles < wg::kNumSMs ? tiles : wg::kNumSMs);
-    wg::inproj_tc_kernel<<<grid, wg::kTcThreads, t.smem_bytes, st>>>(
-        ws_ptr<float>(ws, p.off_u), ws_ptr<float>(ws, p.off_u_lo), ws_ptr<float>(ws, p.off_wp),
-        ws_ptr<float>(ws, p.off_wp_lo), ws_ptr<float>(ws, p.off_bias), ws_ptr<float>(ws, p.off_gi), rows, p.IP, p.GP,
-        t.n_nt, t.N_each, t.stages);
+    wg::inproj_tc2_kernel<<<grid, wg::kT2Threads, t.smem_bytes, st>>>(
+        ws_ptr<float>(ws, p.off_u), ws_ptr<__half>(ws, p.off_wp), ws_ptr<float>(ws, p.off_bias),
+        ws_ptr<float>(ws, p.off_gi), rows, p.IP, t.KP, p.GP, t.n_nt, t.N_each, t.stages);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -449,17 +441,16 @@ bool recur_unit_applies(const Plan& p) {
     return !force_legacy() && wg::recur_u_applies(p.H) &&
            wg::recur_u_smem_floats(p.H, wg::kRuMinR) * 4 <= (size_t)wg::kMaxSmemOptin;
 }
-template <int R, int WPG, bool SAVE>
+template <int R, int WPG, bool SAVE, int HT>
 int launch_recur_unit_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
     const size_t smem = wg::recur_u_smem_floats(p.H, R) * 4;
-    auto kern = wg::gru_recur_unit_kernel<R, WPG, SAVE>;
+    auto kern = wg::gru_recur_unit_kernel<R, WPG, SAVE, HT>;
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_cta = (wg::kRuWarps / WPG) * R;
     const long long grid = (Bc + per_cta - 1) / per_cta;
     if (grid < 1) return WG_OK;
     kern<<<(unsigned)grid, wg::kRuThreads, smem, st>>>(ws_ptr<float>(ws, p.off_gi), ws_ptr<float>(ws, p.off_whu),
-                                                      ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, p.GP, gsave,
-                                                      ldsave);
+                                                      ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, gsave, ldsave);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -468,10 +459,12 @@ int launch_recur_unit(const Plan& p, void* ws, float* out, long long Bc, cudaStr
     const int wpg = wg::recur_u_wpg(p.H);
     int r = recur_u_pick_r(Bc, wg::kRuWarps / wpg);
     while (r > wg::kRuMinR && wg::recur_u_smem_floats(p.H, r) * 4 > (size_t)wg::kMaxSmemOptin) --r;
-#define WG_RU(RR)                                                                                      \
-    case RR:                                                                                           \
-        return wpg == 1 ? launch_recur_unit_t<RR, 1, SAVE>(p, ws, out, Bc, st, gsave, ldsave)          \
-                        : launch_recur_unit_t<RR, 2, SAVE>(p, ws, out, Bc, st, gsave, ldsave);
+    // H = 102 (the shipped 34-station model, 3 x 34) has its own instantiation with compile-time strides
+#define WG_RU(RR)                                                                                          \
+    case RR:                                                                                               \
+        if (p.H == 102) return launch_recur_unit_t<RR, 2, SAVE, 102>(p, ws, out, Bc, st, gsave, ldsave);   \
+        return wpg == 1 ? launch_recur_unit_t<RR, 1, SAVE, 0>(p, ws, out, Bc, st, gsave, ldsave)           \
+                        : launch_recur_unit_t<RR, 2, SAVE, 0>(p, ws, out, Bc, st, gsave, ldsave);
     switch (r) {
         WG_RU(4) WG_RU(5) WG_RU(6) WG_RU(7) WG_RU(8)
     }
@@ -493,7 +486,20 @@ int launch_recur_save(const Plan& p, void* ws, float* out, long long Bc, cudaStr
     return launch_recur_t<16, true, true>(p, ws, out, Bc, st, gsave, ldsave);
 }
 
+int launch_recur_tc(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
+    const size_t smem = wg::recur_tc_smem_bytes(p.H);
+    WG_CUDA(cudaFuncSetAttribute(wg::gru_recur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (Bc + wg::kRtSeqs - 1) / wg::kRtSeqs;
+    if (grid < 1) return WG_OK;
+    wg::gru_recur_tc_kernel<<<(unsigned)grid, wg::kRtThreads, smem, st>>>(
+        ws_ptr<float>(ws, p.off_gi), ws_ptr<__half>(ws, p.off_whh_hi), ws_ptr<__half>(ws, p.off_whh_lo),
+        ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, p.GP);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+
 int launch_recur(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st) {
+    if (p.tc_recur) return launch_recur_tc(p, ws, out, Bc, st);   // the tensor path: one kernel for every batch size
     if (recur_small_applies(p, Bc)) return launch_recur_small<false>(p, ws, out, Bc, st, nullptr, 0);
     if (recur_unit_applies(p)) return launch_recur_unit<false>(p, ws, out, Bc, st, nullptr, 0);
     const size_t smem_ws = wg::recur_smem_floats(p.KP, p.NPR, p.GP, true) * 4;
@@ -505,13 +511,22 @@ int launch_recur(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t
 
 int launch_pack(const Plan& p, void* ws, const float* w_ih, const float* w_hh, const float* b_ih,
                 const float* b_hh, cudaStream_t st) {
-    const int wrows = p.tc ? (p.tcs.NP > p.NPB ? p.tcs.NP : p.NPB) : p.NPB;
+    const int wrows = p.tc ? (p.tc2.NP > p.NPB ? p.tc2.NP : p.NPB) : p.NPB;
     pack_params_kernel<<<wg::kNumSMs * 2, 256, 0, st>>>(
-        w_ih, w_hh, b_ih, b_hh, ws_ptr<float>(ws, p.off_wp), ws_ptr<float>(ws, p.off_wp_lo),
-        ws_ptr<float>(ws, p.off_bias), ws_ptr<float>(ws, p.off_wht),
-        wg::recur_u_applies(p.H) ? ws_ptr<float>(ws, p.off_whu) : nullptr, ws_ptr<float>(ws, p.off_bhn), p.I, p.H, p.IP, p.NPB, p.KP, p.NPR, p.tc ? p.tcs.NP : 0, p.tcs.N_each,
-        wrows > 512 ? wrows : 512);
+        w_ih, w_hh, b_ih, b_hh, ws_ptr<float>(ws, p.off_wp), ws_ptr<float>(ws, p.off_bias),
+        ws_ptr<float>(ws, p.off_wht), wg::recur_u_applies(p.H) ? ws_ptr<float>(ws, p.off_whu) : nullptr,
+        ws_ptr<float>(ws, p.off_bhn), p.I, p.H, p.IP, p.NPB, p.KP, p.NPR, p.tc ? 0 : 1, wrows > 512 ? wrows : 512);
     WG_CUDA(cudaGetLastError());
+    if (p.tc) {
+        wg::pack_wih_tc2_kernel<<<wg::kNumSMs * 2, 256, 0, st>>>(w_ih, ws_ptr<__half>(ws, p.off_wp), p.G, p.I, p.tc2.KP,
+                                                                p.tc2.n_nt, p.tc2.N_each);
+        WG_CUDA(cudaGetLastError());
+    }
+    if (p.tc_recur) {
+        wg::pack_whh_tc_kernel<<<wg::kNumSMs, 256, 0, st>>>(w_hh, ws_ptr<__half>(ws, p.off_whh_hi),
+                                                           ws_ptr<__half>(ws, p.off_whh_lo), p.H);
+        WG_CUDA(cudaGetLastError());
+    }
     return WG_OK;
 }
 
@@ -519,9 +534,8 @@ int launch_pack(const Plan& p, void* ws, const float* w_ih, const float* w_hh, c
 int run_chunk(const Plan& p, void* ws, const float* adj, const float* x, const float* w1, const float* b1,
               const float* w2, const float* b2, float* out, long long Bc, cudaStream_t st) {
     const long long rows = Bc * p.T;
-    int rc = launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_u),
-                                 p.tc ? ws_ptr<float>(ws, p.off_u_lo) : nullptr, rows, p.S, p.Fi, p.Fh, p.Fo, p.IP,
-                                 st);
+    int rc = launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(ws, p.off_u), nullptr, rows, p.S, p.Fi, p.Fh,
+                                 p.Fo, p.IP, st);
     if (rc) return rc;
     rc = launch_inproj(p, ws, rows, st);
     if (rc) return rc;
@@ -754,9 +768,8 @@ int wg_stage_gcn_f32(const float* adj, const float* x, const float* w1, const fl
     if ((rc = check_ws(p, workspace, workspace_bytes))) return rc;
     DeviceGuard g(device);
     WG_CUDA(g.err);
-    return launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(workspace, p.off_u),
-                               p.tc ? ws_ptr<float>(workspace, p.off_u_lo) : nullptr, (long long)Bc * T, S, F_in,
-                               F_hid, F_out, p.IP, static_cast<cudaStream_t>(stream));
+    return launch_gcn<2, true>(x, adj, w1, b1, w2, b2, ws_ptr<float>(workspace, p.off_u), nullptr, (long long)Bc * T, S,
+                               F_in, F_hid, F_out, p.IP, static_cast<cudaStream_t>(stream));
 }
 
 int wg_stage_inproj_f32(int64_t Bc, int T, int S, int F_in, int F_hid, int F_out, int H, int64_t chunk,

@@ -143,7 +143,8 @@ template <int NPW>
 __device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* __restrict__ arow, int astride,
                                          const float* __restrict__ w1d, const float* __restrict__ b1s,
                                          const float* __restrict__ w2d, const float* __restrict__ b2s, int S, int s0,
-                                         int lane, bool row_ok, float* __restrict__ out_col0, int ldo, bool pad_warp) {
+                                         int lane, bool row_ok, float* __restrict__ out_col0, int ldo, bool pad_warp,
+                                         const float* __restrict__ next_src, unsigned next_bytes, uint64_t* bar) {
     const int in_cols = S * kGrF, RS2 = gcn_rows_rs2(S);
     float2 acc[NPW][kGrF];
     // ---- layer 1 ----
@@ -178,7 +179,12 @@ __device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* _
     __syncthreads();   // layer-1 result complete
     // ---- layer 2 ----
     gr_aggregate<NPW, true>(acc, g1row, arow, astride, S, true);
-    __syncthreads();   // the slab may be overwritten by the next block's bulk copy
+    __syncthreads();   // the slab is free: every warp holds its layer-2 aggregate in registers
+    // the next block's bulk copy starts NOW and lands while this block's transform / stores run from registers
+    if (next_bytes != 0 && threadIdx.x == 0) {
+        mbar_expect_tx(bar, next_bytes);
+        bulk_g2s(buf, next_src, next_bytes, bar);
+    }
     auto store_u = [&](const float2 (&o)[NPW][4], int c0, auto width) {
         constexpr int W = decltype(width)::value;
         const float4 bb = *reinterpret_cast<const float4*>(b2s + c0);
@@ -265,16 +271,25 @@ __global__ void __launch_bounds__(kGrMaxWarps * 32, 1)
     const int astride = NW * kGrAP;
     const long long nblocks = (R + kGrRows - 1) / kGrRows;
     unsigned phase = 0;
+    // a block is bulk-copyable when its span is 16-byte aligned and a 16-byte multiple
+    auto block_span = [&](long long rb, const float*& src, unsigned& bytes, int& nrows) {
+        const long long r0 = rb * kGrRows;
+        nrows = (int)((R - r0) < kGrRows ? (R - r0) : kGrRows);
+        src = X + (size_t)r0 * in_cols;
+        bytes = (unsigned)((size_t)nrows * in_cols * 4);
+        return ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0);
+    };
+    bool prefetched = false;   // the current block's bulk copy was issued during the previous block
     for (long long rb = blockIdx.x; rb < nblocks; rb += gridDim.x) {
         const long long r0 = rb * kGrRows;
-        const int nrows = (int)((R - r0) < kGrRows ? (R - r0) : kGrRows);
-        const float* src = X + (size_t)r0 * in_cols;
-        const size_t bytes = (size_t)nrows * in_cols * 4;
-        const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((bytes & 15) == 0);
+        const float* src;
+        unsigned bytes;
+        int nrows;
+        const bool bulk = block_span(rb, src, bytes, nrows);
         if (bulk) {
-            if (tid == 0) {
-                mbar_expect_tx(bar, (unsigned)bytes);
-                bulk_g2s(buf, src, (unsigned)bytes, bar);
+            if (!prefetched && tid == 0) {
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(buf, src, bytes, bar);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
@@ -283,21 +298,28 @@ __global__ void __launch_bounds__(kGrMaxWarps * 32, 1)
             for (int e = tid; e < n_in; e += nthreads) buf[e] = __ldg(src + e);
             __syncthreads();
         }
+        // the block after this one (same CTA): prefetched from inside gr_block when bulk-copyable
+        const float* nsrc = nullptr;
+        unsigned nbytes = 0;
+        int nn;
+        prefetched = false;
+        if (rb + gridDim.x < nblocks && block_span(rb + gridDim.x, nsrc, nbytes, nn)) prefetched = true;
+        else nbytes = 0;
         const long long r = r0 + lane;
         float* out_col0 = out + (size_t)(r / kUTileRows) * ldo * kUTileRows + (r % kUTileRows);
         const bool row_ok = lane < nrows;
         const bool pad_warp = w == NW - 1;
 #define WG_GR(N)                                                                                              \
     case N:                                                                                                   \
-        gr_block<N>(buf, arow, astride, w1d, b1s, w2d, b2s, S, s0, lane, row_ok, out_col0, ldo, pad_warp);    \
+        gr_block<N>(buf, arow, astride, w1d, b1s, w2d, b2s, S, s0, lane, row_ok, out_col0, ldo, pad_warp,     \
+                    nsrc, nbytes, bar);                                                                       \
         break;
         switch (npw) {   // warp-uniform
             WG_GR(1) WG_GR(2) WG_GR(3) WG_GR(4) WG_GR(5)
             default: break;
         }
 #undef WG_GR
-        // gr_block's last barrier already separates this block's reads from the next bulk copy; the
-        // generic-proxy reads are ordered before the async-proxy write by that barrier
+        // gr_block's last barrier separates this block's reads of the slab from the next bulk copy
     }
 }
 

@@ -1,0 +1,269 @@
+// GRU input projection on tcgen05, second generation: fp16 split operands, U read ONCE as fp32.
+//     GI = U . W_ih^T + b,   x = hi + lo with hi = fp16(x), lo = fp16(x - hi)   (22 significant bits)
+//     U.W ~= U_hi.W_hi + U_hi.W_lo + U_lo.W_hi        (kind::f16: fp16 x fp16 products are exact in the
+//                                                      fp32 accumulator; the dropped lo.lo term is 2^-22)
+//
+// Reference: the `gi = W_ih u + b_ih` half of nn.GRU, src/step6_gcn_gru_combined_model.py:11,23.
+//
+// inproj_tc_kernel (first generation, TF32 hi / lo copies of both operands in HBM) moved 11.1 GB from L2
+// for 2.06 GB of algorithmic operand bytes and was L2-bound with the tensor pipe 49 % busy (ncu r01).
+// Here the GCN kernel's ordinary fp32 tiles are the A operand: a stage's [32 k][128 rows] fp32 block
+// arrives by one bulk copy, four converter warps split it into fp16 hi / lo in the UMMA K-major layout
+// in shared memory (never in HBM), and kind::f16 halves both the operand bytes and the MMA time of
+// kind::tf32.  W_ih is pre-split once per call (pack kernel) and streamed from L2 one stage at a time.
+//
+// One persistent CTA per SM, 10 warps:
+//   warp 8       producer: per stage two bulk async copies (A fp32 16 KB, B hi+lo 20 KB at N = 160)
+//   warps 4-7    converters: fp32 -> fp16 hi / lo, 16-byte stores into the canonical layout
+//                ([k / 8][row][8 halves]: 8-row x 16-byte core matrices, SBO = 128 B, LBO = rows * 16 B)
+//   warp 9       MMA issuer: 6 x tcgen05.mma.kind::f16 (M = 128, N <= 160, K = 16) per stage;
+//                hi.hi into one TMEM accumulator, the corrections into a second one (TMEM accumulation
+//                truncates: the small terms are kept apart and added in fp32 in the epilogue)
+//   warps 0-3    epilogue: tcgen05.ld, sum, + bias, 16-byte stores of GI
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "inproj_tc.cuh"
+#include "recur_tc.cuh"
+#include "wg_common.cuh"
+
+namespace wg {
+
+constexpr int kT2BM = 128;
+constexpr int kT2BK = 32;                 // k's per pipeline stage (two MMA k-steps)
+constexpr int kT2Threads = 320;
+constexpr int kT2MaxN = 160;              // gate columns per CTA tile (two accumulators of N columns in TMEM)
+
+struct Tc2Shape {
+    int NP;        // padded gate columns = n_nt * N_each
+    int n_nt;      // column slices
+    int N_each;    // MMA N (multiple of 16)
+    int KP;        // K rounded up to kT2BK
+    int stages;
+    size_t stage_bytes, smem_bytes;
+    bool ok;
+};
+
+__host__ inline Tc2Shape tc2_shape(int G, int I) {
+    Tc2Shape s{};
+    const int np16 = round_up(G, 16);
+    s.n_nt = ceil_div(np16, kT2MaxN);
+    s.N_each = round_up(ceil_div(np16, s.n_nt), 16);
+    s.NP = s.n_nt * s.N_each;
+    s.KP = round_up(I, kT2BK);
+    // A fp32 block + A hi/lo fp16 + B hi/lo fp16
+    s.stage_bytes = (size_t)kT2BM * kT2BK * 4 + (size_t)2 * kT2BM * kT2BK * 2 + (size_t)2 * s.N_each * kT2BK * 2;
+    s.stages = (int)((kMaxSmemOptin - 1024) / s.stage_bytes);
+    if (s.stages > 6) s.stages = 6;
+    s.ok = s.N_each <= kT2MaxN && s.stages >= 2;
+    s.smem_bytes = s.stage_bytes * s.stages + 1024;
+    return s;
+}
+// halves of the packed W_ih (hi and lo together): [n_nt][KP / 32 stages][hi | lo][4 chunks][N_each][8]
+__host__ inline size_t tc2_w_halves(const Tc2Shape& s) { return (size_t)2 * s.NP * s.KP; }
+
+// w_ih [G][I] fp32 -> per (column slice, stage) one contiguous block [hi | lo][k chunk][n][8 halves]
+__global__ void pack_wih_tc2_kernel(const float* __restrict__ w_ih, __half* __restrict__ wp, int G, int I, int KP,
+                                    int n_nt, int N_each) {
+    const long long total = (long long)2 * n_nt * N_each * KP;
+    const int nst = KP / kT2BK;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        long long r = e;
+        const int kk = (int)(r & 7); r >>= 3;
+        const int nl = (int)(r % N_each); r /= N_each;
+        const int c = (int)(r & 3); r >>= 2;
+        const int part = (int)(r & 1); r >>= 1;
+        const int kb = (int)(r % nst), nt = (int)(r / nst);
+        const int n = nt * N_each + nl, k = kb * kT2BK + c * 8 + kk;
+        const float v = (n < G && k < I) ? w_ih[(size_t)n * I + k] : 0.0f;
+        const __half h = __float2half_rn(v);
+        wp[e] = part == 0 ? h : __float2half_rn(v - __half2float(h));
+    }
+}
+
+// A: U tiles [M/128][lda][128] fp32 (lda >= KP, K-major 128-row tiles written by the GCN kernels);
+// Wp: pack_wih_tc2_kernel's output;  C: [M][ldc] row-major (GI)
+__global__ void __launch_bounds__(kT2Threads, 1)
+    inproj_tc2_kernel(const float* __restrict__ A, const __half* __restrict__ Wp, const float* __restrict__ bias,
+                      float* __restrict__ C, long long M, int lda, int KP, int ldc, int n_nt, int N_each, int stages) {
+    extern __shared__ __align__(1024) unsigned char smem_t2[];
+    const uint32_t a32_bytes = kT2BM * kT2BK * 4;                   // 16 KB
+    const uint32_t a16_bytes = kT2BM * kT2BK * 2;                   // 8 KB per part
+    const uint32_t b_bytes = (uint32_t)N_each * kT2BK * 2;          // per part
+    const uint32_t stage_bytes = a32_bytes + 2 * a16_bytes + 2 * b_bytes;
+    unsigned char* tail = smem_t2 + (size_t)stage_bytes * stages;
+    uint64_t* full_ld = reinterpret_cast<uint64_t*>(tail);           // [stages] bulk copies landed
+    uint64_t* full_cv = full_ld + 8;                                  // [stages] A converted
+    uint64_t* empty_bar = full_cv + 8;                                // [stages] MMAs have read the stage
+    uint64_t* tmem_full = empty_bar + 8;
+    uint64_t* tmem_empty = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long m_tiles = (M + kT2BM - 1) / kT2BM;
+    const long long n_tiles = m_tiles * n_nt;   // tile = mt * n_nt + nt: the slices of one row tile run together
+    const int KB = KP / kT2BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_ld[s], 1);
+            mbar_init(&full_cv[s], 4);   // one arrival per converter warp
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);        // one arrival per epilogue warp
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_cols = (uint32_t)N_each;   // accumulators: [0, N) hi.hi, [N, 2N) corrections
+
+    if (warp == 8) {
+        // ===================== producer =====================
+        int s = 0;
+        uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long mt = tile / n_nt;
+            const int nt = (int)(tile - mt * n_nt);
+            const float* a = A + (size_t)mt * lda * kT2BM;
+            const __half* b = Wp + (size_t)nt * KB * 2 * N_each * kT2BK;
+            for (int kb = 0; kb < KB; ++kb) {
+                if (lane == 0) {
+                    mbar_wait(&empty_bar[s], phase ^ 1);  // slot free (first pass: passes immediately)
+                    unsigned char* st = smem_t2 + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full_ld[s], a32_bytes + 2 * b_bytes);
+                    bulk_g2s(st, a + (size_t)kb * kT2BK * kT2BM, a32_bytes, &full_ld[s]);
+                    bulk_g2s(st + a32_bytes + 2 * a16_bytes, b + (size_t)kb * 2 * N_each * kT2BK, 2 * b_bytes,
+                             &full_ld[s]);
+                }
+                __syncwarp();
+                if (++s == stages) { s = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== converters: thread = row =====================
+        const int r = tid - 128;
+        int s = 0;
+        uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&full_ld[s], phase);
+                unsigned char* st = smem_t2 + (size_t)s * stage_bytes;
+                const float* a32 = reinterpret_cast<const float*>(st) + r;          // [k][128 rows]
+                unsigned char* hi = st + a32_bytes + r * 16;                         // [chunk][128 rows][8 halves]
+                unsigned char* lo = hi + a16_bytes;
+#pragma unroll
+                for (int c = 0; c < kT2BK / 8; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) v[kk] = a32[(c * 8 + kk) * kT2BM];
+                    __half2 h[4], l[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+                        const float2 back = __half22float2(h[q]);
+                        l[q] = __floats2half2_rn(v[2 * q] - back.x, v[2 * q + 1] - back.y);
+                    }
+                    *reinterpret_cast<uint4*>(hi + c * (kT2BM * 16)) = *reinterpret_cast<uint4*>(h);
+                    *reinterpret_cast<uint4*>(lo + c * (kT2BM * 16)) = *reinterpret_cast<uint4*>(l);
+                }
+                fence_async_smem();   // the converted operand is read by the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_cv[s]);
+                if (++s == stages) { s = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc_f16(kT2BM, N_each);
+        const uint32_t lbo_a = kT2BM * 16, lbo_b = (uint32_t)N_each * 16, sbo = 128;
+        int s = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (lane == 0) {
+                mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the accumulators
+                tc_fence_after();
+            }
+            __syncwarp();
+            for (int kb = 0; kb < KB; ++kb) {
+                if (lane == 0) {
+                    mbar_wait(&full_ld[s], phase);     // B landed (async proxy)
+                    mbar_wait(&full_cv[s], phase);     // A converted
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem_t2 + (size_t)s * stage_bytes);
+                    const uint32_t sa_hi = st + a32_bytes, sa_lo = sa_hi + a16_bytes;
+                    const uint32_t sb_hi = sa_lo + a16_bytes, sb_lo = sb_hi + b_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < kT2BK / 16; ++ks) {     // K = 16 per MMA: two 16-byte chunks
+                        const uint64_t da_hi = umma_desc_kmajor(sa_hi + ks * 2 * lbo_a, lbo_a, sbo);
+                        const uint64_t da_lo = umma_desc_kmajor(sa_lo + ks * 2 * lbo_a, lbo_a, sbo);
+                        const uint64_t db_hi = umma_desc_kmajor(sb_hi + ks * 2 * lbo_b, lbo_b, sbo);
+                        const uint64_t db_lo = umma_desc_kmajor(sb_lo + ks * 2 * lbo_b, lbo_b, sbo);
+                        umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | ks) != 0);             // hi . hi
+                        umma_f16(tmem_base + acc_cols, da_hi, db_lo, idesc, (kb | ks) != 0);  // hi . lo
+                        umma_f16(tmem_base + acc_cols, da_lo, db_hi, idesc, 1);               // lo . hi
+                    }
+                    umma_commit(&empty_bar[s]);                  // stage free once these MMAs have read it
+                    if (kb == KB - 1) umma_commit(tmem_full);    // accumulators complete
+                }
+                __syncwarp();
+                if (++s == stages) { s = 0; phase ^= 1; }
+            }
+            acc_phase ^= 1;
+        }
+    } else {
+        // ===================== epilogue (warps 0-3 <-> TMEM lanes 32w .. 32w+31) =====================
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long mt = tile / n_nt;
+            const int nt = (int)(tile - mt * n_nt);
+            mbar_wait(tmem_full, acc_phase);
+            tc_fence_after();
+            const long long row = mt * kT2BM + warp * 32 + lane;
+            float* crow = C + (size_t)(row < M ? row : 0) * ldc;
+            const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < N_each; c0 += 32) {
+                float v0[32], v1[32];
+                tmem_ld32(lane_base + c0, v0);
+                tmem_ld32(lane_base + acc_cols + c0, v1);
+                if (row < M) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int cl = c0 + 4 * q;            // column inside the slice
+                        const int c = nt * N_each + cl;       // gate column
+                        if (cl < N_each && c < ldc) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+                            float4 o;
+                            o.x = (v0[4 * q] + v1[4 * q]) + b4.x;
+                            o.y = (v0[4 * q + 1] + v1[4 * q + 1]) + b4.y;
+                            o.z = (v0[4 * q + 2] + v1[4 * q + 2]) + b4.z;
+                            o.w = (v0[4 * q + 3] + v1[4 * q + 3]) + b4.w;
+                            *reinterpret_cast<float4*>(crow + c) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+}  // namespace wg

@@ -11,9 +11,9 @@
 // Here a thread owns the r, z and n columns of TWO hidden units (2p, 2p+1) for the R sequences of
 // its group:   acc[i][g] (float2 over the unit pair)  +=  h[i][k] * (W_g[k][2p], W_g[k][2p+1])
 // — FFMA2 with h as the broadcast scalar.  When the product is done the thread already holds
-// everything a GRU cell needs for its R x 2 (sequence, unit) items: gi arrives in thread-private
-// shared-memory slots (cp.async, issued one step ahead by the thread that consumes them), the
-// previous state of those items lives in registers.  No merge phase, no gh round trip; the only
+// everything a GRU cell needs for its R x 2 (sequence, unit) items: gi of the step sits in a per-group
+// shared-memory tile (one bulk async copy per sequence row, issued one step ahead by one thread and
+// completing on the group's mbarrier), the previous state of those items lives in registers.  No merge phase, no gh round trip; the only
 // exchange per step is the new state, written to the other half of a double-buffered h tile,
 // followed by ONE named barrier among the group's warps.
 //
@@ -45,15 +45,14 @@ __host__ __device__ inline bool recur_u_applies(int H) { return recur_u_hp2(H) /
 __host__ __device__ inline int recur_u_hs_stride(int KP) { return ((KP / 4) & 1) ? KP : KP + 4; }
 __host__ __device__ inline size_t recur_u_smem_floats(int H, int R) {
     const int KP = round_up(H, 4), HP2 = recur_u_hp2(H), WPG = recur_u_wpg(H), NGRP = kRuWarps / WPG;
+    const int GP = round_up(3 * H, 4);
     size_t n = (size_t)KP * 3 * HP2;                          // W_hh^T as [k][gate][unit]
+    n = round_up((int)n, 4);
     n += 2 * (size_t)NGRP * R * recur_u_hs_stride(KP);        // h, double buffered
-    n += (size_t)NGRP * 3 * R * WPG * 32 * 2;                 // gi slots (float2 per thread, gate, row)
-    n += (size_t)HP2;                                         // b_hn
+    n += (size_t)NGRP * R * GP;                               // gi tile of the current step, per group
+    n += (size_t)round_up(HP2, 4);                            // b_hn
+    n += 2 * kRuWarps;                                        // one mbarrier per group
     return n;
-}
-
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 
 #ifdef WG_RC_TRACE
@@ -73,23 +72,27 @@ struct RuFrag {
     float2 w[4][3];   // w[kk][g] = W_g[k + kk][2p .. 2p+1]
 };
 
-// GI  [B*T][ldg]   gi with b_ih (+ b_hh for r, z) folded in, column g*H + j
+// GI  [B*T][ldg]   gi with b_ih (+ b_hh for r, z) folded in, column g*H + j; ldg = 3H rounded up to 4
 // Whu [KP][3][HP2] W_hh^T, Whu[k][g][j] = w_hh[g*H + j][k], zero padded
 // out [B][T][H];   gsave (SAVE): [B*T][ldsave] = [r | z | n | W_hn h + b_hn]
-template <int R, int WPG, bool SAVE>
+// HT > 0: the hidden size is the compile-time constant HT (every shared-memory offset becomes an
+// immediate); HT == 0: H is the runtime argument.
+template <int R, int WPG, bool SAVE, int HT>
 __global__ void __launch_bounds__(kRuThreads, 1)
     gru_recur_unit_kernel(const float* __restrict__ GI, const float* __restrict__ Whu, const float* __restrict__ bhn,
-                          float* __restrict__ out, long long B, int T, int H, int ldg,
+                          float* __restrict__ out, long long B, int T, int H_rt,
                           float* __restrict__ gsave, int ldsave) {
     constexpr int NGRP = kRuWarps / WPG;   // groups per CTA
     constexpr int NG = WPG * 32;           // threads per group
     extern __shared__ __align__(16) float smem[];
-    const int KP = round_up(H, 4), HP2 = recur_u_hp2(H), NS = HP2 >> 1;
+    const int H = HT > 0 ? HT : H_rt;
+    const int KP = round_up(H, 4), HP2 = recur_u_hp2(H), NS = HP2 >> 1, ldg = round_up(3 * H, 4);
     const int RS = recur_u_hs_stride(KP);
-    float* Ws = smem;                                        // [KP][3][HP2]
-    float* hs = Ws + (size_t)KP * 3 * HP2;                   // [2][NGRP * R][RS]
-    float2* gis = reinterpret_cast<float2*>(hs + 2 * (size_t)NGRP * R * RS);   // [NGRP][3 * R][NG]
-    float* bns = reinterpret_cast<float*>(gis + (size_t)NGRP * 3 * R * NG);    // [HP2]
+    float* Ws = smem;                                                // [KP][3][HP2]
+    float* hs = Ws + round_up(KP * 3 * HP2, 4);                      // [2][NGRP * R][RS]
+    float* gis = hs + 2 * NGRP * R * RS;                             // [NGRP][R][ldg]
+    float* bns = gis + NGRP * R * ldg;                               // [HP2]
+    uint64_t* gbar = reinterpret_cast<uint64_t*>(bns + round_up(HP2, 4));   // [NGRP]
 
     const int tid = threadIdx.x;
     const int grp = tid / NG;
@@ -100,6 +103,8 @@ __global__ void __launch_bounds__(kRuThreads, 1)
     const bool has1 = j0 + 1 < H;          // the pair's second unit exists (H odd: not in the last slot)
     const long long b0 = (long long)blockIdx.x * (NGRP * R) + grp * R;   // first sequence of the group
     const int H2 = 2 * H;
+    const long long left = B - b0;
+    const int nvalid = left >= R ? R : (left > 0 ? (int)left : 0);       // sequences of this group that exist
 
     {
         const int n4 = KP * 3 * HP2 / 4;   // KP % 4 == 0
@@ -108,38 +113,25 @@ __global__ void __launch_bounds__(kRuThreads, 1)
         for (int e = tid; e < n4; e += kRuThreads) dst[e] = __ldg(src + e);
     }
     for (int e = tid; e < 2 * NGRP * R * RS; e += kRuThreads) hs[e] = 0.0f;
-    for (int e = tid; e < NGRP * 3 * R * NG; e += kRuThreads) gis[e] = make_float2(0.0f, 0.0f);
+    for (int e = tid; e < NGRP * R * ldg; e += kRuThreads) gis[e] = 0.0f;
     for (int e = tid; e < HP2; e += kRuThreads) bns[e] = e < H ? __ldg(bhn + e) : 0.0f;
+    if (tid < NGRP) mbar_init(&gbar[tid], 1);
+    if (tid == 0) fence_mbar_init();
 
-    // this thread's gi slots: gis[grp][g * R + i][p]; 8-byte copies where the source is 8-byte aligned
-    float2* myslots = gis + ((size_t)grp * 3 * R) * NG + p;
-    const bool gi_vec = (reinterpret_cast<uintptr_t>(GI) & 7) == 0 && (ldg & 1) == 0;
-    auto prefetch_gi = [&](int t) {
-        if (active) {
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                const int col = g * H + j0;
-                const bool v8 = gi_vec && has1 && ((col & 1) == 0);
-#pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    if (b0 + i < B) {
-                        const float* src = GI + ((size_t)(b0 + i) * T + t) * ldg + col;
-                        float2* dst = myslots + (g * R + i) * NG;
-                        if (v8) {
-                            cp_async8(dst, src);
-                        } else {
-                            cp_async4(&dst->x, src);
-                            if (has1) cp_async4(&dst->y, src + 1);
-                        }
-                    }
-                }
-            }
+    // gi(t) of the group's sequences: one bulk async copy per row (ldg * 4 bytes, 16-byte multiple) into the
+    // group's tile, completion counted on the group's mbarrier.  Issued by one thread AFTER the group barrier
+    // that ends step t-1, i.e. when every thread of the group has read gi(t-1).
+    float* gi_tile = gis + grp * R * ldg;
+    auto fetch_gi = [&](int t) {
+        if (nvalid > 0) {
+            mbar_expect_tx(&gbar[grp], (unsigned)(nvalid * ldg * 4));
+            for (int i = 0; i < nvalid; ++i)
+                bulk_g2s(gi_tile + i * ldg, GI + ((size_t)(b0 + i) * T + t) * ldg, (unsigned)(ldg * 4), &gbar[grp]);
         }
-        cp_async_commit();
     };
 
-    __syncthreads();   // zero fills are done before any async copy may land
-    prefetch_gi(0);
+    __syncthreads();   // zero fills and barrier inits are done before any async copy may land
+    if (p == 0) fetch_gi(0);
 
     float2 hprev[R];   // h_{t-1} of this thread's items
 #pragma unroll
@@ -148,10 +140,16 @@ __global__ void __launch_bounds__(kRuThreads, 1)
     const float* wbase = Ws + j0;
     const bool out_vec = (reinterpret_cast<uintptr_t>(out) & 7) == 0 && (H & 1) == 0;
     const bool save_vec = SAVE && (reinterpret_cast<uintptr_t>(gsave) & 7) == 0 && (ldsave & 1) == 0 && (H & 1) == 0;
+    const bool gi_vec = (H & 1) == 0;      // g*H + j0 even: 8-byte reads of the gi tile
+    // running output pointers: + H per step
+    float* op0 = out + (size_t)b0 * T * H + j0;
+    const size_t o_seq = (size_t)T * H;
+    float* gs0 = SAVE ? gsave + (size_t)b0 * T * ldsave + j0 : nullptr;
+    const size_t s_seq = (size_t)T * ldsave;
 
     for (int t = 0; t < T; ++t) {
-        const float* hcur = hs + ((size_t)(t & 1) * NGRP + grp) * R * RS;          // h_{t-1}: read
-        float* hnxt = hs + ((size_t)((t + 1) & 1) * NGRP + grp) * R * RS;          // h_t: written
+        const float* hcur = hs + ((t & 1) * NGRP + grp) * R * RS;           // h_{t-1}: read
+        float* hnxt = hs + (((t + 1) & 1) * NGRP + grp) * R * RS;           // h_t: written
         WG_RU_TRACE(0);
         // ================= product: acc[i][g] = sum_k h[i][k] * W_g[k][2p, 2p+1] =================
         float2 acc[R][3];
@@ -207,13 +205,20 @@ __global__ void __launch_bounds__(kRuThreads, 1)
         }
         WG_RU_TRACE(1);
         // ================= gates, straight from the accumulators =================
-        cp_async_wait<0>();   // this thread's gi(t) slots have landed
+        if (nvalid > 0) mbar_wait(&gbar[grp], (unsigned)(t & 1));   // gi(t) has landed
         float2 gi[3][R];
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int i = 0; i < R; ++i) gi[g][i] = myslots[(g * R + i) * NG];
-        if (t + 1 < T) prefetch_gi(t + 1);   // the slots are free again; lands during the next product
+            for (int i = 0; i < R; ++i) {
+                const float* gp = gi_tile + i * ldg + g * H + j0;
+                if (gi_vec) {
+                    gi[g][i] = *reinterpret_cast<const float2*>(gp);
+                } else {
+                    gi[g][i].x = gp[0];
+                    gi[g][i].y = has1 ? gp[1] : 0.0f;
+                }
+            }
         WG_RU_TRACE(2);
 #pragma unroll
         for (int i = 0; i < R; ++i) {
@@ -232,8 +237,8 @@ __global__ void __launch_bounds__(kRuThreads, 1)
             hprev[i] = hnew;
             if (active) {
                 *reinterpret_cast<float2*>(hnxt + i * RS + j0) = hnew;
-                if (b0 + i < B) {
-                    float* op = out + ((size_t)(b0 + i) * T + t) * H + j0;
+                if (i < nvalid) {
+                    float* op = op0 + i * o_seq;
                     if (out_vec) {
                         *reinterpret_cast<float2*>(op) = hnew;
                     } else {
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(kRuThreads, 1)
                         if (has1) op[1] = hnew.y;
                     }
                     if (SAVE) {
-                        float* gs = gsave + ((size_t)(b0 + i) * T + t) * ldsave + j0;
+                        float* gs = gs0 + i * s_seq;
                         if (save_vec) {
                             *reinterpret_cast<float2*>(gs) = r;
                             *reinterpret_cast<float2*>(gs + H) = z;
@@ -255,10 +260,14 @@ __global__ void __launch_bounds__(kRuThreads, 1)
                 }
             }
         }
+        op0 += H;
+        if (SAVE) gs0 += ldsave;
         // h_t complete for the group before anyone reads it; the buffer written at step t+1 is the one
-        // read at step t, which every warp of the group has finished with once it arrives here
+        // read at step t, which every warp of the group has finished with once it arrives here.  The same
+        // barrier tells the fetching thread that everyone has read gi(t).
         WG_RU_TRACE(3);
         group_barrier(1 + grp, NG);
+        if (p == 0 && t + 1 < T) fetch_gi(t + 1);   // lands during the next product
         WG_RU_TRACE(4);
     }
 }
