@@ -206,3 +206,15 @@ def test_reference_copy_reproduces_the_goldens_bit_for_bit():
         assert np.array_equal(y.numpy(), g["y_ref_f32"])        # the very code that made the goldens
         yb = reference_forward_batched(model, adj, x)
         assert normalised_max_error(yb.numpy(), g["y_ref_f32"]) < 3e-6
+
+
+def test_oracle_matches_reference_class_at_wide_dims():
+    """fwd_wide.npz: the reference class GCN_GRU(13, 128, 13, 3900, 128) on a 300-station kNN graph."""
+    from conftest import golden
+
+    g = golden("fwd_wide.npz")
+    sd = {k.replace("__", "."): g[k] for k in g.files if "__" in k}
+    assert sd["gru.weight_ih_l0"].shape == (384, 3900) and sd["conv1.weight"].shape == (13, 128)
+    y = gcn_gru_forward(g["adj"], g["x"], sd, dtype=np.float32)
+    assert normalised_max_error(y, g["y_ref_f32"]) <= 3e-6
+    assert normalised_max_error(gcn_gru_forward(g["adj"], g["x"], sd, dtype=np.float64), g["y_ref_f64"]) <= 1e-12

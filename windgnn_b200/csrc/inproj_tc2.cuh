@@ -8,15 +8,16 @@
 // inproj_tc_kernel (first generation, TF32 hi / lo copies of both operands in HBM) moved 11.1 GB from L2
 // for 2.06 GB of algorithmic operand bytes and was L2-bound with the tensor pipe 49 % busy (ncu r01).
 // Here the GCN kernel's ordinary fp32 tiles are the A operand: a stage's [32 k][128 rows] fp32 block
-// arrives by one bulk copy, four converter warps split it into fp16 hi / lo in the UMMA K-major layout
+// arrives by one bulk copy, eight converter warps split it into fp16 hi / lo in the UMMA K-major layout
 // in shared memory (never in HBM), and kind::f16 halves both the operand bytes and the MMA time of
 // kind::tf32.  W_ih is pre-split once per call (pack kernel) and streamed from L2 one stage at a time.
 //
-// One persistent CTA per SM, 10 warps:
-//   warp 8       producer: per stage two bulk async copies (A fp32 16 KB, B hi+lo 20 KB at N = 160)
-//   warps 4-7    converters: fp32 -> fp16 hi / lo, 16-byte stores into the canonical layout
-//                ([k / 8][row][8 halves]: 8-row x 16-byte core matrices, SBO = 128 B, LBO = rows * 16 B)
-//   warp 9       MMA issuer: 6 x tcgen05.mma.kind::f16 (M = 128, N <= 160, K = 16) per stage;
+// One persistent CTA per SM, 14 warps:
+//   warp 12      producer: per stage two bulk async copies (A fp32 16 KB, B hi+lo 20 KB at N = 160)
+//   warps 4-11   converters: a thread takes 2 rows x 8 k's (8-byte loads), splits fp32 -> fp16 hi / lo and
+//                writes 16-byte chunks into the canonical layout ([k / 8][row][8 halves]: 8-row x 16-byte
+//                core matrices, SBO = 128 B, LBO = rows * 16 B)
+//   warp 13      MMA issuer: 6 x tcgen05.mma.kind::f16 (M = 128, N <= 160, K = 16) per stage;
 //                hi.hi into one TMEM accumulator, the corrections into a second one (TMEM accumulation
 //                truncates: the small terms are kept apart and added in fp32 in the epilogue)
 //   warps 0-3    epilogue: tcgen05.ld, sum, + bias, 16-byte stores of GI
@@ -32,7 +33,8 @@ namespace wg {
 
 constexpr int kT2BM = 128;
 constexpr int kT2BK = 32;                 // k's per pipeline stage (two MMA k-steps)
-constexpr int kT2Threads = 320;
+constexpr int kT2ConvWarps = 8;
+constexpr int kT2Threads = (4 + kT2ConvWarps + 2) * 32;   // epilogue, converters, producer, MMA issuer
 constexpr int kT2MaxN = 160;              // gate columns per CTA tile (two accumulators of N columns in TMEM)
 
 struct Tc2Shape {
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_ld[s], 1);
-            mbar_init(&full_cv[s], 4);   // one arrival per converter warp
+            mbar_init(&full_cv[s], kT2ConvWarps);   // one arrival per converter warp
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc_cols = (uint32_t)N_each;   // accumulators: [0, N) hi.hi, [N, 2N) corrections
 
-    if (warp == 8) {
+    if (warp == 4 + kT2ConvWarps) {
         // ===================== producer =====================
         int s = 0;
         uint32_t phase = 0;
@@ -149,40 +151,42 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                 if (++s == stages) { s = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================== converters: thread = row =====================
-        const int r = tid - 128;
+    } else if (warp >= 4 && warp < 4 + kT2ConvWarps) {
+        // ===================== converters: thread = (row pair, 8-k chunk) =====================
+        const int ct = tid - 128;                 // 0 .. 255
+        const int rp = ct & 63, c = ct >> 6;      // rows 2 rp, 2 rp + 1; k's 8 c .. 8 c + 7 of the stage
         int s = 0;
         uint32_t phase = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(&full_ld[s], phase);
                 unsigned char* st = smem_t2 + (size_t)s * stage_bytes;
-                const float* a32 = reinterpret_cast<const float*>(st) + r;          // [k][128 rows]
-                unsigned char* hi = st + a32_bytes + r * 16;                         // [chunk][128 rows][8 halves]
+                const float* a32 = reinterpret_cast<const float*>(st) + (c * 8) * kT2BM + 2 * rp;   // [k][128 rows]
+                unsigned char* hi = st + a32_bytes + c * (kT2BM * 16) + (2 * rp) * 16;             // [chunk][row][8 halves]
                 unsigned char* lo = hi + a16_bytes;
+                float2 v[8];
 #pragma unroll
-                for (int c = 0; c < kT2BK / 8; ++c) {
-                    float v[8];
+                for (int kk = 0; kk < 8; ++kk) v[kk] = *reinterpret_cast<const float2*>(a32 + kk * kT2BM);
+                __half2 h0[4], l0[4], h1[4], l1[4];   // row 2 rp / row 2 rp + 1: k pairs
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) v[kk] = a32[(c * 8 + kk) * kT2BM];
-                    __half2 h[4], l[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-                        const float2 back = __half22float2(h[q]);
-                        l[q] = __floats2half2_rn(v[2 * q] - back.x, v[2 * q + 1] - back.y);
-                    }
-                    *reinterpret_cast<uint4*>(hi + c * (kT2BM * 16)) = *reinterpret_cast<uint4*>(h);
-                    *reinterpret_cast<uint4*>(lo + c * (kT2BM * 16)) = *reinterpret_cast<uint4*>(l);
+                for (int q = 0; q < 4; ++q) {
+                    h0[q] = __floats2half2_rn(v[2 * q].x, v[2 * q + 1].x);
+                    h1[q] = __floats2half2_rn(v[2 * q].y, v[2 * q + 1].y);
+                    const float2 b0 = __half22float2(h0[q]), b1 = __half22float2(h1[q]);
+                    l0[q] = __floats2half2_rn(v[2 * q].x - b0.x, v[2 * q + 1].x - b0.y);
+                    l1[q] = __floats2half2_rn(v[2 * q].y - b1.x, v[2 * q + 1].y - b1.y);
                 }
+                *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<uint4*>(h0);
+                *reinterpret_cast<uint4*>(hi + 16) = *reinterpret_cast<uint4*>(h1);
+                *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<uint4*>(l0);
+                *reinterpret_cast<uint4*>(lo + 16) = *reinterpret_cast<uint4*>(l1);
                 fence_async_smem();   // the converted operand is read by the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_cv[s]);
                 if (++s == stages) { s = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 4 + kT2ConvWarps + 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = umma_idesc_f16(kT2BM, N_each);
         const uint32_t lbo_a = kT2BM * 16, lbo_b = (uint32_t)N_each * 16, sbo = 128;

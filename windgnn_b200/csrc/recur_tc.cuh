@@ -21,10 +21,14 @@
 // UMMA canonical K-major layout, 2-byte stores; the 16-byte K chunks are 16 bytes further apart than
 // they need to be so that the four chunks a warp writes hit different banks).
 //
-// A CTA = 4 gate warps (TMEM lanes 0..127 = hidden units) + 1 MMA-issuer warp, W_hh (hi + lo, 172 KB
-// at H = 102) resident in shared memory, two groups of 16 sequences: while the gate warps work on
-// one group the tensor core runs the other group's 63 MMAs, so the product's latency is hidden and a
-// step costs the gate math (MUFU-bound) only.
+// A CTA holds W_hh (hi + lo, 172 KB at H = 102) in shared memory and runs two independent groups of 16
+// sequences.  A group = 8 warps: warps 0-3 (TMEM lanes 0..127 = hidden units) take its sequences 0-7,
+// warps 4-7 its sequences 8-15.  Per step the group's warps do the gate math, write h_t, meet at a named
+// barrier, ONE thread of the group issues the 42 MMAs of the next step and commits them to the group's
+// mbarrier, on which all eight warps then wait (their next gi values are already in flight).  The two
+// groups never synchronise with each other, so one group's product (tensor pipe) overlaps the other's
+// gate math (MUFU / ALU).  The hi.hi and hi.lo products share one N = 32 MMA (B rows = h_hi | h_lo), so
+// A_hi is read from shared memory once for both.
 //
 // The same kernel serves every batch size in the tensor path (a result never depends on how a batch
 // is split: the columns of an MMA are independent).
@@ -33,14 +37,15 @@
 #include <cuda_fp16.h>
 
 #include "inproj_tc.cuh"
+#include "recur.cuh"
 #include "wg_common.cuh"
 
 namespace wg {
 
 constexpr int kRtN = 16;        // sequences per group
-constexpr int kRtGroups = 2;    // groups per CTA: one warpgroup of gate warps each
-constexpr int kRtGateWarps = 4 * kRtGroups;
-constexpr int kRtThreads = (kRtGateWarps + 1) * 32;
+constexpr int kRtGroups = 2;    // groups per CTA
+constexpr int kRtGroupWarps = 8;          // warps per group: two sets of 4 (TMEM lane quarters), 8 sequences each
+constexpr int kRtThreads = kRtGroups * kRtGroupWarps * 32;
 constexpr int kRtSeqs = kRtN * kRtGroups;
 // B operand of a group: rows 0..15 = h_hi of its sequences, rows 16..31 = h_lo; 16-byte K chunks are
 // (32 rows + 1) * 16 bytes apart (the extra 16 bytes spread the chunks a warp writes over the banks)
@@ -122,10 +127,9 @@ __global__ void __launch_bounds__(kRtThreads, 1)
     unsigned char* sA = smem_rt;                                   // [hi | lo][gate][chunk][128][8 halves]
     unsigned char* sB = sA + 2 * a_part;                           // [group][chunk][hi rows | lo rows][8 halves]
     uint64_t* acc_full = reinterpret_cast<uint64_t*>(sB + kRtGroups * b_grp);        // [groups]
-    uint64_t* h_ready = acc_full + kRtGroups;                                         // [groups]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + kRtGroups);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + kRtGroups);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const long long b0 = (long long)blockIdx.x * kRtSeqs;
 
     // ---- stage W_hh (hi, lo) and zero the state operand ----
@@ -142,10 +146,7 @@ __global__ void __launch_bounds__(kRtThreads, 1)
         for (int e = tid; e < (int)(kRtGroups * b_grp / 4); e += kRtThreads) z[e] = 0u;
     }
     if (tid == 0) {
-        for (int g = 0; g < kRtGroups; ++g) {
-            mbar_init(&acc_full[g], 1);
-            mbar_init(&h_ready[g], 4);   // one arrival per gate warp of the group
-        }
+        for (int g = 0; g < kRtGroups; ++g) mbar_init(&acc_full[g], 1);
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -162,127 +163,120 @@ __global__ void __launch_bounds__(kRtThreads, 1)
     // the corrections.  One N = 32 MMA (B rows = h_hi | h_lo) writes both with a single read of A_hi; the
     // lo.hi product (A_lo, B rows = h_hi, N = 16) is accumulated onto the correction columns.
 
-    if (warp == kRtGateWarps) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc32 = umma_idesc_f16(128, 2 * kRtN), idesc16 = umma_idesc_f16(128, kRtN);
-            const uint32_t sa = smem_u32(sA), sb = smem_u32(sB);
-            uint32_t ph[kRtGroups] = {0, 0};
-            for (int t = 1; t < T; ++t) {            // step t needs h_{t-1}; at t = 0 the product is zero
-                for (int g = 0; g < kRtGroups; ++g) {
-                    mbar_wait(&h_ready[g], ph[g]);   // h_{t-1} of group g is in shared memory, accumulators drained
-                    ph[g] ^= 1;
-                    tc_fence_after();
-                    const uint32_t bg = sb + (uint32_t)g * b_grp;
-                    const uint32_t dcol = tmem_base + (uint32_t)(g * 6 * kRtN);
-                    for (int q = 0; q < 3; ++q) {
-                        const uint32_t ah = sa + (uint32_t)q * NCH * 2048, al = ah + a_part;
-                        for (int ks = 0; ks < NKS; ++ks) {
-                            const uint64_t da_hi = umma_desc_kmajor(ah + ks * 2 * 2048, 2048, 128);
-                            const uint64_t da_lo = umma_desc_kmajor(al + ks * 2 * 2048, 2048, 128);
-                            const uint64_t db = umma_desc_kmajor(bg + ks * 2 * kRtBLbo, kRtBLbo, 128);
-                            umma_f16(dcol + q * 2 * kRtN, da_hi, db, idesc32, ks != 0);           // hi.hi | hi.lo
-                            umma_f16(dcol + q * 2 * kRtN + kRtN, da_lo, db, idesc16, 1);          // lo.hi
-                        }
-                    }
-                    umma_commit(&acc_full[g]);
-                }
-            }
-        }
-        __syncwarp();
-    } else {
-        // ===================== gate warps: warpgroup g owns group g; TMEM lane j = hidden unit j =====================
-        const int g = warp >> 2;
-        const int j = tid & 127;
-        const bool unit_ok = j < H;
-        const int jc = unit_ok ? j : H - 1;
-        const float bn = __ldg(bhn + jc);
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 6 * kRtN);
-        // byte address of this unit inside the group's B operand: chunk j / 8, element j % 8 (row n adds n * 16)
-        unsigned char* bh = sB + (size_t)g * b_grp + (size_t)(jc >> 3) * kRtBLbo + (size_t)(jc & 7) * 2;
-        unsigned char* bl = bh + kRtN * 16;
-        float hprev[kRtN];
+    const int g = warp / kRtGroupWarps;                   // group of this warp
+    const int gt = tid - g * kRtGroupWarps * 32;          // thread index inside the group, 0 .. 255
+    const int half = gt >> 7;                             // sequences 8 half .. 8 half + 7 of the group
+    const int j = gt & 127;                               // hidden unit = TMEM lane
+    const bool unit_ok = j < H;
+    const int jc = unit_ok ? j : H - 1;
+    const float bn = __ldg(bhn + jc);
+    const uint32_t tcol = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 6 * kRtN + half * 8);
+    // byte address of this unit inside the group's B operand: chunk j / 8, element j % 8 (row n adds n * 16)
+    unsigned char* bh = sB + (size_t)g * b_grp + (size_t)(jc >> 3) * kRtBLbo + (size_t)(jc & 7) * 2 + half * 8 * 16;
+    unsigned char* bl = bh + kRtN * 16;
+    float hprev[8];
 #pragma unroll
-        for (int n = 0; n < kRtN; ++n) hprev[n] = 0.0f;
-        const int H2 = 2 * H;
-        const long long bg0 = b0 + g * kRtN;
-        const long long left = B - bg0;
-        const int nvalid = left >= kRtN ? kRtN : (left > 0 ? (int)left : 0);
-        // running pointers (advance one step at a time); sequences are T * ldg / T * H floats apart
-        const float* gp = GI + (size_t)bg0 * T * ldg + jc;
-        float* op = out + (size_t)bg0 * T * H + j;
-        const int g_seq = T * ldg, o_seq = T * H;
-        uint32_t ph = 0;
+    for (int n = 0; n < 8; ++n) hprev[n] = 0.0f;
+    const int H2 = 2 * H;
+    const long long bg0 = b0 + g * kRtN + half * 8;       // first sequence of this thread
+    const long long left = B - bg0;
+    const int nvalid = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
+    // running pointers (advance one step at a time); sequences are T * ldg / T * H floats apart
+    const float* gp = GI + (size_t)bg0 * T * ldg + jc;
+    float* op = out + (size_t)bg0 * T * H + j;
+    const int g_seq = T * ldg, o_seq = T * H;
+    uint32_t ph = 0;
+    // MMA issue (one thread per group): operand bases
+    const uint32_t idesc32 = umma_idesc_f16(128, 2 * kRtN), idesc16 = umma_idesc_f16(128, kRtN);
+    const uint32_t sa = smem_u32(sA), sbg = smem_u32(sB) + (uint32_t)g * b_grp;
+    const uint32_t dcol = tmem_base + (uint32_t)(g * 6 * kRtN);
 
-        // gi of 8 sequences (one half group): [gate][seq]; rows beyond B are readable scratch (never stored)
-        auto load_gi = [&](float (&gi)[3][8], const float* p) {
+    // gi of this thread's 8 sequences: [gate][seq]; rows beyond B are readable scratch (never stored)
+    auto load_gi = [&](float (&gi)[3][8], const float* p) {
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            gi[0][n] = __ldg(p + n * g_seq);
+            gi[1][n] = __ldg(p + n * g_seq + H);
+            gi[2][n] = __ldg(p + n * g_seq + H2);
+        }
+    };
+    float gi[3][8], gi_nxt[3][8];
+    load_gi(gi, gp);
+    for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) load_gi(gi_nxt, gp + ldg);   // a whole step ahead: lands during this step's gates + product
+        float rr[8], zz[8], hn[8];
+        if (t > 0) {
+            mbar_wait(&acc_full[g], ph);   // this group's product of step t is complete
+            ph ^= 1;
+            tc_fence_after();
+            float m[8], c[8];
+            tmem_ld8(tcol, m);
+            tmem_ld8(tcol + kRtN, c);
+            tmem_ld_wait(m);
+            tmem_ld_wait(c);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) rr[n] = gi[0][n] + (m[n] + c[n]);
+            tmem_ld8(tcol + 2 * kRtN, m);
+            tmem_ld8(tcol + 3 * kRtN, c);
+            tmem_ld_wait(m);
+            tmem_ld_wait(c);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) zz[n] = gi[1][n] + (m[n] + c[n]);
+            tmem_ld8(tcol + 4 * kRtN, m);
+            tmem_ld8(tcol + 5 * kRtN, c);
+            tmem_ld_wait(m);
+            tmem_ld_wait(c);
+#pragma unroll
+            for (int n = 0; n < 8; ++n) hn[n] = (m[n] + c[n]) + bn;
+            tc_fence_before();   // the accumulators have been read: the next product may overwrite them
+        } else {
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                gi[0][n] = __ldg(p + n * g_seq);
-                gi[1][n] = __ldg(p + n * g_seq + H);
-                gi[2][n] = __ldg(p + n * g_seq + H2);
+                rr[n] = gi[0][n];
+                zz[n] = gi[1][n];
+                hn[n] = bn;
             }
-        };
-        float gi_cur[3][8], gi_nxt[3][8];
-        load_gi(gi_cur, gp);
-        for (int t = 0; t < T; ++t) {
-            if (t > 0) {
-                mbar_wait(&acc_full[g], ph);   // this group's product of step t is complete
-                ph ^= 1;
-                tc_fence_after();
+        }
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float r = sigmoid_f(rr[n]);
+            const float z = sigmoid_f(zz[n]);
+            const float nv = tanh_f(gi[2][n] + r * hn[n]);
+            const float hnew = (hprev[n] - nv) * z + nv;
+            hprev[n] = hnew;
+            if (unit_ok) {
+                const __half hh = __float2half_rn(hnew);
+                const __half hl = __float2half_rn(hnew - __half2float(hh));
+                *reinterpret_cast<__half*>(bh + n * 16) = hh;
+                *reinterpret_cast<__half*>(bl + n * 16) = hl;
+                if (n < nvalid) op[n * o_seq] = hnew;
             }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                // prefetch the gi of the next half group (this step's second half, or the next step's first)
-                if (half == 0) load_gi(gi_nxt, gp + 8 * g_seq);
-                else if (t + 1 < T) load_gi(gi_nxt, gp + ldg);
-                float m[3][8], c[3][8];
-                if (t > 0) {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        tmem_ld8(lane_base + q * 2 * kRtN + half * 8, m[q]);
-                        tmem_ld8(lane_base + q * 2 * kRtN + kRtN + half * 8, c[q]);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        tmem_ld_wait(m[q]);
-                        tmem_ld_wait(c[q]);
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q)
-#pragma unroll
-                        for (int n = 0; n < 8; ++n) m[q][n] = c[q][n] = 0.0f;
-                }
-#pragma unroll
-                for (int n = 0; n < 8; ++n) {
-                    const int nn = half * 8 + n;
-                    const float r = sigmoid_f(gi_cur[0][n] + (m[0][n] + c[0][n]));
-                    const float z = sigmoid_f(gi_cur[1][n] + (m[1][n] + c[1][n]));
-                    const float hn = (m[2][n] + c[2][n]) + bn;
-                    const float nv = tanh_f(gi_cur[2][n] + r * hn);
-                    const float hnew = (hprev[nn] - nv) * z + nv;
-                    hprev[nn] = hnew;
-                    if (unit_ok) {
-                        const __half hh = __float2half_rn(hnew);
-                        const __half hl = __float2half_rn(hnew - __half2float(hh));
-                        *reinterpret_cast<__half*>(bh + nn * 16) = hh;
-                        *reinterpret_cast<__half*>(bl + nn * 16) = hl;
-                        if (nn < nvalid) op[nn * o_seq] = hnew;
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-#pragma unroll
-                    for (int n = 0; n < 8; ++n) gi_cur[q][n] = gi_nxt[q][n];
-            }
-            gp += ldg;
-            op += H;
-            // h_t of the group is in shared memory and its accumulators have been read: hand both to the issuer
-            tc_fence_before();
+        }
+        gp += ldg;
+        op += H;
+        if (t + 1 < T) {
+            // h_t of the group is in shared memory (generic-proxy writes -> visible to the tensor core), every
+            // warp of the group has read its accumulators: one thread issues the next step's product
             fence_async_smem();
-            __syncwarp();
-            if (lane == 0 && t + 1 < T) mbar_arrive(&h_ready[g]);
+            group_barrier(1 + g, kRtGroupWarps * 32);
+            if (gt == 0) {
+                tc_fence_after();
+                for (int q = 0; q < 3; ++q) {
+                    const uint32_t ah = sa + (uint32_t)q * NCH * 2048, al = ah + a_part;
+                    for (int ks = 0; ks < NKS; ++ks) {
+                        const uint64_t da_hi = umma_desc_kmajor(ah + ks * 2 * 2048, 2048, 128);
+                        const uint64_t da_lo = umma_desc_kmajor(al + ks * 2 * 2048, 2048, 128);
+                        const uint64_t db = umma_desc_kmajor(sbg + ks * 2 * kRtBLbo, kRtBLbo, 128);
+                        umma_f16(dcol + q * 2 * kRtN, da_hi, db, idesc32, ks != 0);           // hi.hi | hi.lo
+                        umma_f16(dcol + q * 2 * kRtN + kRtN, da_lo, db, idesc16, 1);          // lo.hi
+                    }
+                }
+                umma_commit(&acc_full[g]);
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int n = 0; n < 8; ++n) gi[q][n] = gi_nxt[q][n];
         }
     }
     tc_fence_before();

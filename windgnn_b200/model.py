@@ -71,8 +71,9 @@ class GCN_GRU(nn.Module):
         self.conv2 = GraphConvLayer(hidden_dim, output_dim)
         self.gru = nn.GRU(gru_input, gru_hidden_dim, batch_first=True)
         self.chunk = 0  # sequences per internal pass; 0 = library default
-        # "fp32": every contraction as FP32 FMA.  "tf32x3": the GRU input projection on the tcgen05
-        # tensor cores with error-compensated TF32 (same 1e-5 parity bar, see inproj_tc.cuh)
+        # "fp32": every contraction as FP32 FMA.  "tensor": the GRU input projection and the recurrent product
+        # on the tcgen05 tensor cores with error-compensated fp16 split operands (same 1e-5 parity bar, see
+        # inproj_tc2.cuh / recur_tc.cuh)
         self.precision = "fp32"
         self._csr_cache = None  # (key, (rowptr, colidx, vals)) of the last large adjacency seen
 
@@ -131,6 +132,6 @@ class GCN_GRU(nn.Module):
 
         if self.precision == "fp32":
             return 0
-        if self.precision == "tf32x3":
+        if self.precision in ("tensor", "tf32x3"):   # "tf32x3": the round-1 name of the tensor path
             return _lib.FLAG_TENSOR_CORES
-        raise ValueError(f"precision must be 'fp32' or 'tf32x3', got {self.precision!r}")
+        raise ValueError(f"precision must be 'fp32' or 'tensor', got {self.precision!r}")
