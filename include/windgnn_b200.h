@@ -10,8 +10,8 @@
  *   - "device pointer" = memory of CUDA device `device`; the call is asynchronous
  *     on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).
  *   - The caller owns every buffer, including `workspace`; the library keeps no
- *     pointer after the call returns and has no global mutable state besides the
- *     thread-local last-error string.
+ *     pointer after the call returns.  Its only state is thread-local: the last-error
+ *     string and, for the host-buffer entry points, a cache of internal streams / events.
  *   - Return value: 0 (WG_OK) on success, a negative WG_ERR_* code otherwise;
  *     `wg_last_error()` then describes the failure.  Nothing throws.
  *   - There is no CPU fallback: without a CUDA device every compute entry point
@@ -27,10 +27,10 @@
 extern "C" {
 #endif
 
-#define WG_ABI_VERSION 3
+#define WG_ABI_VERSION 4
 
 /* `flags` of the GCN-GRU entry points */
-#define WG_FLAG_TENSOR_CORES 1 /* input projection on tcgen05 with error-compensated TF32 (3xTF32) */
+#define WG_FLAG_TENSOR_CORES 1 /* GRU input projection and recurrent product on tcgen05 (split fp16 operands) */
 
 enum {
     WG_OK = 0,
@@ -65,10 +65,13 @@ const char* wg_last_error(void);
  *
  * `chunk` = sequences processed per internal pass (bounds the workspace); 0 = default.
  * `flags`: 0 = every contraction as FP32 FMA (the reference's arithmetic, different summation
- *   order).  WG_FLAG_TENSOR_CORES = the GRU input projection (65 % of the FLOPs) runs on the
- *   tcgen05 tensor cores as three TF32 products per term (hi*hi + hi*lo + lo*hi, fp32
- *   accumulate); its error against fp64 is the same size as the FP32 path's and it is held to
- *   the same 1e-5 parity bar.  Needs 3H <= 512.  The workspace must be sized with the same flags.
+ *   order).  WG_FLAG_TENSOR_CORES = the GRU input projection (65 % of the FLOPs) and, for H <= 128,
+ *   the recurrent product h.W_hh^T run on the tcgen05 tensor cores: each operand is split into two
+ *   fp16 parts (x = hi + lo, 22 significant bits) and a product is hi*hi + hi*lo + lo*hi with fp32
+ *   accumulation; the error against fp64 is the same size as the FP32 path's and the path is held
+ *   to the same 1e-5 parity bar.  Operand magnitudes must stay inside the fp16 range (|x| < 65504;
+ *   the GCN outputs and the weights of the shipped models are O(1)).  Results do not depend on how
+ *   a batch is split.  The workspace must be sized with the same flags.
  * ---------------------------------------------------------------------------------- */
 size_t wg_gcn_gru_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
                                   int64_t chunk, int flags);
@@ -85,12 +88,12 @@ int wg_gcn_gru_forward_f32(const float* adj, const float* x, const float* w1, co
  * 4096-station kNN configuration; the dense entry point above is the tuned path for the shipped
  * 7- / 34-station models. */
 size_t wg_gcn_gru_csr_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
-                                      int64_t chunk);
+                                      int64_t chunk, int flags);
 int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
                                const float* x, const float* w1, const float* b1, const float* w2,
                                const float* b2, const float* w_ih, const float* w_hh, const float* b_ih,
                                const float* b_hh, float* out, int64_t B, int T, int S, int F_in,
-                               int F_hid, int F_out, int H, int64_t chunk, void* workspace,
+                               int F_hid, int F_out, int H, int64_t chunk, int flags, void* workspace,
                                size_t workspace_bytes, int device, void* stream);
 
 /* Same computation with HOST buffers for x (pinned for full overlap) and out: the batch is
@@ -110,6 +113,18 @@ int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const flo
                                 const float* b_hh, float* out_host, int64_t B, int T, int S,
                                 int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags,
                                 void* workspace, size_t workspace_bytes, int device);
+
+/* The evaluation loop of src/main.py:101-116 in one call: the same host-buffer pipeline, but only what the
+ * reference's statistics read leaves the GPU — the LAST timestep of every window, de-normalised,
+ *   pred_host [B, H] = out[:, T-1, :] * (vmax - vmin) + vmin      (src/main.py:103,116,131,146)
+ * i.e. 3S floats per window instead of T*3S.  Workspace: wg_gcn_gru_host_workspace_bytes. */
+int wg_gcn_gru_predict_host_f32(const float* adj, const float* x_host, const float* w1,
+                                const float* b1, const float* w2, const float* b2,
+                                const float* w_ih, const float* w_hh, const float* b_ih,
+                                const float* b_hh, float* pred_host, int64_t B, int T, int S,
+                                int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags,
+                                double vmin, double vmax, void* workspace, size_t workspace_bytes,
+                                int device);
 
 /* ------------------------------------------------------------------------------------
  * Single GCN layer — replaces `GraphConvLayer.forward(adj_matrix, attr_matrix)`
@@ -161,6 +176,18 @@ size_t wg_build_graph_workspace_bytes(int S, int k);
 int wg_build_graph_f64(const double* xy, double* adj_f64, float* adj_f32, int S, int k,
                        void* workspace, size_t workspace_bytes, int device, void* stream);
 
+/* The same kNN graph (k > 0) straight into CSR, without any S x S matrix (the form
+ * wg_gcn_gru_forward_csr_f32 takes; src/step2_graph_builder.py:24-38 builds the dense matrix):
+ *   rowptr  int32 [S + 1] out     colidx  int32 [capacity] out, ascending within a row
+ *   vals_f64 / vals_f32 [capacity] out (either may be NULL): bit-identical to the non-zeros of
+ *             wg_build_graph_f64's matrix (an exact zero never changes a column sum)
+ *   capacity  >= S * (2k + 1) entries (an upper bound of the symmetrised pattern incl. self loops);
+ *             the number of stored entries is rowptr[S]. */
+size_t wg_build_graph_csr_workspace_bytes(int S, int k);
+int wg_build_graph_csr_f64(const double* xy, int S, int k, int32_t* rowptr, int32_t* colidx,
+                           double* vals_f64, float* vals_f32, int64_t capacity, void* workspace,
+                           size_t workspace_bytes, int device, void* stream);
+
 /* Deterministic synthetic station coordinates (SplitMix64 stream):
  *   latlon [S, 2] fp64 device out, uniform in the shipped stations' bounding box. */
 int wg_synthetic_coordinates_f64(double* latlon, int S, uint64_t seed, int device, void* stream);
@@ -180,6 +207,16 @@ int wg_synthetic_coordinates_f64(double* latlon, int S, uint64_t seed, int devic
  * (src/main.py:103) restricted to the last timestep the evaluation reads (main.py:116,131,146):
  *   out [B, T, H] -> pred [B, H], fp32 arithmetic with NumPy's two roundings.
  * ---------------------------------------------------------------------------------- */
+/* Pivot of the long table — replaces the per-station stacking loop of `generate_sequences`
+ * (src/step4_sequence_preparer.py:36-47):
+ *   station int32 [n_rows] device: rank of each row's station name in np.unique order (:38)
+ *   values  [n_rows, F] fp32 device: the numeric columns 2:15 of the long table, file order
+ *   table   [Ttot, S, F] out: table[t][s] = the t-th row (file order) of station s
+ *   counts  int32 [S] out: rows found per station (the reference requires them all equal; rows
+ *           beyond Ttot are not stored). */
+int wg_pivot_table_f32(const int32_t* station, const float* values, float* table, int32_t* counts,
+                       int64_t n_rows, int S, int F, int64_t Ttot, int device, void* stream);
+
 int64_t wg_num_windows(int64_t Ttot, int L, int horizons);
 int wg_make_windows_f32(const float* table, const int64_t* perm, float* x, float* y, int64_t Ttot, int S,
                         int F, int L, int label_f, int horizons, int64_t N, int device, void* stream);

@@ -25,4 +25,4 @@ from .graph_oracle import (  # noqa: F401
     knn_graph_f64,
     synthetic_coordinates,
 )
-from .windows_oracle import create_sequences, denorm_last_step  # noqa: F401,E402
+from .windows_oracle import create_sequences, denorm_last_step, pivot_long_table  # noqa: F401,E402

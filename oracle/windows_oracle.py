@@ -37,3 +37,13 @@ def denorm_last_step(outputs, wind_min, wind_max):
     outputs = np.asarray(outputs, dtype=np.float32)
     full = outputs * (wind_max - wind_min) + wind_min  # main.py:103
     return full[:, -1, :]
+
+
+def pivot_long_table(long_table):
+    """step4:36-47 — ``long_table [n_rows, C]`` (column 0 = station) -> ``[time, station, C]``: stations in
+    ``np.unique`` order (:38), each station's rows in file order (:41), stacked along a new axis 1 (:42-47)."""
+    import numpy as np
+
+    stations = np.unique(long_table[:, 0])
+    cols = [long_table[np.where(long_table[:, 0] == st)] for st in stations]
+    return np.stack(cols, axis=1), stations

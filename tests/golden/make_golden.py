@@ -21,6 +21,8 @@ What it writes (all small, all committed):
                          300-station kNN(8) graph (dense matrix, as the reference takes it), B = 2, T = 6, with its
                          parameters: pins the CSR path, which re-associates layer 2 as ``A.(G1.W2)``
                          (``python tests/golden/make_golden.py --only-wide`` writes just this file)
+``pivot.npz``            the reference's own ``generate_sequences`` (pivot + split + windows) on a small interleaved
+                         long table (``--only-pivot`` writes just this file)
 ``manifest.json``        sha256 of every file + library versions
 """
 
@@ -77,6 +79,31 @@ def make_windows_golden():
     np.savez_compressed(os.path.join(HERE, "windows.npz"), table=table, x=x, y=y, indices=idx, seq_length=L)
 
 
+def make_pivot_golden():
+    """``pivot.npz``: the reference's own ``generate_sequences`` (step4:30-74: pivot, 70/30 split, windows) on a
+    small long table whose rows are interleaved by station and whose station names are NOT in alphabetical
+    order of first appearance.  Saved: the long table, and the tensors the reference's loaders serve."""
+    import step4_sequence_preparer as step4
+
+    rng = np.random.default_rng(2024)
+    names = ["Verger AGDM", "Bassano AGCM", "Rosemary IMCIN"]       # first-appearance order != np.unique order
+    n_t = 600                                                       # 420 train rows (2 windows), 180 test rows (1)
+    rows = []
+    for t in range(n_t):
+        for st in (names if t % 2 == 0 else names[::-1]):           # file order of the stations varies per hour
+            rows.append([st, f"2021-01-01 {t:05d}"] + list(rng.random(13).astype(np.float32).astype(np.float64)))
+    long_table = np.array(rows, dtype=object)
+    np.random.seed(777)
+    train_loader, test_loader, num_attr, num_stations = step4.generate_sequences(long_table, 168, "cpu")
+    tr_x, tr_y = train_loader.dataset.tensors
+    te_x, te_y = test_loader.dataset.tensors
+    assert num_attr == 13 and num_stations == 3
+    np.savez_compressed(os.path.join(HERE, "pivot.npz"), station=long_table[:, 0].astype(str),
+                        values=long_table[:, 2:].astype(np.float64), train_x=tr_x.numpy(), train_y=tr_y.numpy(),
+                        test_x=te_x.numpy(), test_y=te_y.numpy(), seed=777)
+    print("pivot.npz: train", tuple(tr_x.shape), tuple(tr_y.shape), "test", tuple(te_x.shape), tuple(te_y.shape))
+
+
 def make_wide_golden():
     """``fwd_wide.npz``: the unmodified reference class at wide dims (hidden 128, GRU hidden 128) on a
     300-station kNN graph.  The graph comes from the oracle's kNN generator (the reference has none);
@@ -117,12 +144,17 @@ def update_manifest_entry(fn):
 
 
 def main():
+    if "--only-pivot" in sys.argv:
+        make_pivot_golden()
+        update_manifest_entry("pivot.npz")
+        return
     if "--only-wide" in sys.argv:
         torch.set_num_threads(1)
         make_wide_golden()
         update_manifest_entry("fwd_wide.npz")
         return
     make_windows_golden()
+    make_pivot_golden()
     make_wide_golden()
     torch.manual_seed(0)
     np.random.seed(0)

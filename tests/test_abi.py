@@ -25,7 +25,7 @@ def test_library_builds_and_loads():
     path = build.build()
     assert os.path.exists(path)
     lib = _lib.load()
-    assert lib.wg_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.wg_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_every_declared_symbol_is_exported():
@@ -54,8 +54,12 @@ def test_workspace_planning():
     assert lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 4096, 0) > 2 * big
     assert lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 0, 0) == lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 256, 0)
     assert lib.wg_gcn_gru_host_workspace_bytes(4096, *dims34, 0, 0) < big
-    # the tensor-core path keeps U and w_ih as hi + lo parts: more scratch; unknown flags are rejected
-    assert lib.wg_gcn_gru_workspace_bytes(4096, *dims34, 0, _lib.FLAG_TENSOR_CORES) > big
+    # the tensor-core path reads the same fp32 U tiles (no hi / lo copies in HBM): its scratch differs only by
+    # the packed fp16 weights; unknown flags are rejected
+    tc = lib.wg_gcn_gru_workspace_bytes(4096, *dims34, 0, _lib.FLAG_TENSOR_CORES)
+    assert 0 < abs(tc - big) < 4 << 20
+    assert lib.wg_gcn_gru_csr_workspace_bytes(256, 24, 4096, 13, 128, 13, 128, 0, _lib.FLAG_TENSOR_CORES) > 0
+    assert lib.wg_build_graph_csr_workspace_bytes(4096, 8) < lib.wg_build_graph_workspace_bytes(4096, 8) // 20
     assert lib.wg_gcn_gru_workspace_bytes(4096, *dims34, 0, 8) == 0
     assert lib.wg_gcn_gru_workspace_bytes(8, 0, 34, 13, 13, 13, 102, 0, 0) == 0  # T = 0 is invalid
     assert "non-positive" in _lib.last_error()

@@ -209,6 +209,20 @@ def test_host_buffer_path_matches_device_path(full34):
         model.chunk = 0
     assert out.shape == (1500, 168, 102) and not out.is_cuda
     assert torch.equal(out, y[:1500].cpu())
+    # second call on the same thread reuses the cached internal streams / events
+    assert torch.equal(model.forward_host(adj, xh), out)
+
+
+def test_host_predict_returns_only_the_denormalised_last_step(full34):
+    """wg_gcn_gru_predict_host_f32: the evaluation loop of main.py:101-116 in one call — only 3S floats per
+    window come back; bit-identical to the full host forward followed by the library's de-normalisation."""
+    model, adj, x, y = full34
+    xh = x[:700].cpu().pin_memory()
+    wmin, wmax = 0.0, 83.6
+    pred = model.forward_host(adj, xh, last_step_range=(wmin, wmax))
+    assert pred.shape == (700, 102) and not pred.is_cuda
+    ref = windgnn_b200.denormalise_last_step(y[:700], wmin, wmax).cpu()
+    assert torch.equal(pred, ref)
 
 
 def test_stage_entry_points_compose(full34):

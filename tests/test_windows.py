@@ -7,7 +7,7 @@ import torch
 
 import windgnn_b200
 from conftest import golden
-from oracle import create_sequences, denorm_last_step
+from oracle import create_sequences, denorm_last_step, pivot_long_table
 from windgnn_b200 import _lib
 
 DEV = "cuda:0"
@@ -91,3 +91,50 @@ def test_denormalise_last_step_bit_exact():
     assert np.array_equal(pred, denorm_last_step(out, wmin, wmax))
     one = windgnn_b200.denormalise_last_step(torch.from_numpy(out[0]).to(DEV), wmin, wmax)   # [T, H] like the reference
     assert one.shape == (1, 21)
+
+
+def _pivot_golden_long_table():
+    g = golden("pivot.npz")
+    n = len(g["station"])
+    lt = np.concatenate([g["station"].astype(object)[:, None], np.zeros((n, 1), dtype=object),
+                         g["values"].astype(object)], axis=1)
+    return g, lt
+
+
+def test_oracle_pivot_and_windows_match_reference_generate_sequences():
+    """pivot.npz was produced by the reference's own generate_sequences (step4:30-74) on an interleaved long
+    table: oracle pivot (step4:36-47) + 70/30 split (:50) + oracle windows (:7-27) reproduce its loaders."""
+    g, lt = _pivot_golden_long_table()
+    tab, stations = pivot_long_table(lt)
+    assert tab.shape == (600, 3, 15) and list(stations) == sorted(set(g["station"]))
+    n_test = int(np.ceil(0.3 * tab.shape[0]))
+    n_train = tab.shape[0] - n_test
+    np.random.seed(int(g["seed"]))                    # the reference shuffles train windows first, then test
+    for part, data in (("train", tab[:n_train]), ("test", tab[n_train:])):
+        idx = np.arange(len(data) // 168)
+        np.random.shuffle(idx)
+        x, y = create_sequences(data, 168, idx)
+        assert np.array_equal(x.astype(np.float32), g[f"{part}_x"])
+        assert np.array_equal(y.astype(np.float32), g[f"{part}_y"])
+
+
+@pytest.mark.gpu
+def test_device_pivot_bit_exact_vs_reference_golden():
+    g, lt = _pivot_golden_long_table()
+    values = torch.from_numpy(g["values"].astype(np.float32)).to(DEV)
+    table, stations = windgnn_b200.pivot_long_table(g["station"], values)
+    ref, ref_st = pivot_long_table(lt)
+    assert list(stations) == list(ref_st)
+    assert torch.equal(table.cpu(), torch.from_numpy(ref[:, :, 2:].astype(np.float32)))
+    # and the whole step4 chain on the device against the reference's loaders: split, windows, labels
+    n_test = int(np.ceil(0.3 * table.shape[0]))
+    n_train = table.shape[0] - n_test
+    np.random.seed(int(g["seed"]))
+    for part, data in (("train", table[:n_train]), ("test", table[n_train:])):
+        idx = np.arange(data.shape[0] // 168)
+        np.random.shuffle(idx)
+        x, y = windgnn_b200.create_sequences(data.contiguous(), 168, perm=torch.from_numpy(idx).to(DEV))
+        assert torch.equal(x.cpu(), torch.from_numpy(g[f"{part}_x"]))
+        assert torch.equal(y.cpu(), torch.from_numpy(g[f"{part}_y"]))
+    with pytest.raises(RuntimeError, match="split evenly|unequal"):
+        windgnn_b200.pivot_long_table(g["station"][:-1], values[:-1])

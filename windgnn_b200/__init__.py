@@ -14,16 +14,23 @@ CUDA device is present.
 from . import _lib, ops  # noqa: F401
 from .model import GCN_GRU, GraphConvLayer  # noqa: F401
 from .graph import (  # noqa: F401
+    CsrGraph,
     build_graph,
     build_graph_from_latlon,
+    knn_graph_csr,
+    knn_graph_csr_from_latlon,
     knn_graph_from_latlon,
     mercator,
     synthetic_coordinates,
 )
 
-from .sequences import create_sequences, denormalise_last_step, num_windows  # noqa: F401
+from .sequences import create_sequences, denormalise_last_step, num_windows, pivot_long_table  # noqa: F401
 
 __all__ = [
+    "pivot_long_table",
+    "CsrGraph",
+    "knn_graph_csr",
+    "knn_graph_csr_from_latlon",
     "create_sequences",
     "denormalise_last_step",
     "num_windows",

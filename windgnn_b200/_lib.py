@@ -19,7 +19,7 @@ WG_ERR_BAD_ARG = -1
 WG_ERR_UNSUPPORTED = -2
 WG_ERR_WORKSPACE = -3
 WG_ERR_CUDA = -4
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_TENSOR_CORES = 1
 
 
@@ -39,10 +39,12 @@ _SIGNATURES = {
     "wg_last_error": (c_char_p, []),
     "wg_gcn_gru_workspace_bytes": (c_size_t, [c_int64, *_DIMS, c_int64, c_int]),
     "wg_gcn_gru_forward_f32": (c_int, [_P] * 11 + [c_int64, *_DIMS, c_int64, c_int, _P, c_size_t, c_int, _P]),
-    "wg_gcn_gru_csr_workspace_bytes": (c_size_t, [c_int64, *_DIMS, c_int64]),
-    "wg_gcn_gru_forward_csr_f32": (c_int, [_P] * 13 + [c_int64, *_DIMS, c_int64, _P, c_size_t, c_int, _P]),
+    "wg_gcn_gru_csr_workspace_bytes": (c_size_t, [c_int64, *_DIMS, c_int64, c_int]),
+    "wg_gcn_gru_forward_csr_f32": (c_int, [_P] * 13 + [c_int64, *_DIMS, c_int64, c_int, _P, c_size_t, c_int, _P]),
     "wg_gcn_gru_host_workspace_bytes": (c_size_t, [c_int64, *_DIMS, c_int64, c_int]),
     "wg_gcn_gru_forward_host_f32": (c_int, [_P] * 11 + [c_int64, *_DIMS, c_int64, c_int, _P, c_size_t, c_int]),
+    "wg_gcn_gru_predict_host_f32": (c_int, [_P] * 11 + [c_int64, *_DIMS, c_int64, c_int, c_double, c_double, _P,
+                                            c_size_t, c_int]),
     "wg_gcn_layer_f32": (c_int, [_P] * 5 + [c_int64, c_int, c_int, c_int, c_int, _P]),
     "wg_stage_pack_f32": (c_int, [_P] * 4 + [*_DIMS, c_int64, c_int, _P, c_size_t, c_int, _P]),
     "wg_stage_gcn_f32": (c_int, [_P] * 6 + [c_int64, *_DIMS, c_int64, c_int, _P, c_size_t, c_int, _P]),
@@ -50,7 +52,10 @@ _SIGNATURES = {
     "wg_stage_recur_f32": (c_int, [_P, c_int64, *_DIMS, c_int64, c_int, _P, c_size_t, c_int, _P]),
     "wg_build_graph_workspace_bytes": (c_size_t, [c_int, c_int]),
     "wg_build_graph_f64": (c_int, [_P, _P, _P, c_int, c_int, _P, c_size_t, c_int, _P]),
+    "wg_build_graph_csr_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "wg_build_graph_csr_f64": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int64, _P, c_size_t, c_int, _P]),
     "wg_synthetic_coordinates_f64": (c_int, [_P, c_int, c_uint64, c_int, _P]),
+    "wg_pivot_table_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int64, c_int, _P]),
     "wg_num_windows": (c_int64, [c_int64, c_int, c_int]),
     "wg_make_windows_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, _P]),
     "wg_denorm_last_step_f32": (c_int, [_P, _P, c_int64, c_int, c_int, c_double, c_double, c_int, _P]),

@@ -102,10 +102,10 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     if (flags & ~WG_FLAG_TENSOR_CORES) return fail(WG_ERR_BAD_ARG, "unknown flags 0x%x", flags);
     p.I = S * Fo;
     p.G = 3 * H;
-    // tensor-core projection (inproj_tc2.cuh): only on the dense small-graph path and when two accumulators of
-    // the gate slice fit TMEM; it consumes the same fp32 U tiles, K padded to its 32-k stage
+    // tensor-core projection (inproj_tc2.cuh): when two accumulators of the gate slice fit TMEM; it consumes the
+    // same fp32 U tiles (dense or CSR graph path alike), K padded to its 32-k stage
     p.tc2 = wg::tc2_shape(p.G, p.I);
-    p.tc = (flags & WG_FLAG_TENSOR_CORES) != 0 && !sparse;
+    p.tc = (flags & WG_FLAG_TENSOR_CORES) != 0;
     if (p.tc && !p.tc2.ok)
         return fail(WG_ERR_UNSUPPORTED, "tensor-core projection: unsupported gate width 3H = %d", p.G);
     p.IP = p.tc ? p.tc2.KP : wg::round_up(p.I, wg::kIpBK);
@@ -824,9 +824,9 @@ int wg_gcn_gru_forward_f32(const float* adj, const float* x, const float* w1, co
 }
 
 size_t wg_gcn_gru_csr_workspace_bytes(int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
-                                      int64_t chunk) {
+                                      int64_t chunk, int flags) {
     Plan p;
-    if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, true)) return 0;
+    if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, true, flags)) return 0;
     return p.total;
 }
 
@@ -834,10 +834,10 @@ int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, con
                                const float* w1, const float* b1, const float* w2, const float* b2,
                                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                                float* out, int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H,
-                               int64_t chunk, void* workspace, size_t workspace_bytes, int device,
+                               int64_t chunk, int flags, void* workspace, size_t workspace_bytes, int device,
                                void* stream) {
     Plan p;
-    int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, true);
+    int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, true, flags);
     if (rc) return rc;
     if (B == 0) return WG_OK;
     if (any_null({rowptr, colidx, vals, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, out}))
@@ -873,56 +873,81 @@ size_t wg_gcn_gru_host_workspace_bytes(int64_t B, int T, int S, int F_in, int F_
     if (make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, false, flags)) return 0;
     const size_t xs = align_up((size_t)p.chunk * T * S * F_in * 4);
     const size_t os = align_up((size_t)p.chunk * T * H * 4);
-    return kHostLanes * align_up(p.total) + kHostSlots * (xs + os);
+    const size_t ps = align_up((size_t)p.chunk * H * 4);   // de-normalised last step (wg_gcn_gru_predict_host_f32)
+    return kHostLanes * align_up(p.total) + kHostSlots * (xs + os + ps);
 }
 
-int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const float* w1, const float* b1,
-                                const float* w2, const float* b2, const float* w_ih, const float* w_hh,
-                                const float* b_ih, const float* b_hh, float* out_host, int64_t B, int T,
-                                int S, int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags,
-                                void* workspace, size_t workspace_bytes, int device) {
+}  // extern "C"
+
+namespace {
+
+// Internal streams and events of the host-buffer entry points: created once per (host thread, device) and
+// reused by every later call of that thread (creating 4 streams + 9 events per call cost ~0.1 ms).
+struct HostCtx {
+    bool ready = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[kHostLanes] = {};
+    cudaEvent_t ev_in[kHostSlots] = {}, ev_cmp[kHostSlots] = {}, ev_out[kHostSlots] = {};
+};
+constexpr int kMaxDevices = 64;
+thread_local HostCtx g_host_ctx[kMaxDevices];
+
+int host_ctx(int device, HostCtx** out) {
+    if (device < 0 || device >= kMaxDevices) return fail(WG_ERR_BAD_ARG, "device index %d out of range", device);
+    HostCtx& c = g_host_ctx[device];
+    if (!c.ready) {
+        WG_CUDA(cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking));
+        WG_CUDA(cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking));
+        for (int l = 0; l < kHostLanes; ++l) WG_CUDA(cudaStreamCreateWithFlags(&c.s_cmp[l], cudaStreamNonBlocking));
+        for (int i = 0; i < kHostSlots; ++i) {
+            WG_CUDA(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
+            WG_CUDA(cudaEventCreateWithFlags(&c.ev_cmp[i], cudaEventDisableTiming));
+            WG_CUDA(cudaEventCreateWithFlags(&c.ev_out[i], cudaEventDisableTiming));
+        }
+        c.ready = true;
+    }
+    *out = &c;
+    return WG_OK;
+}
+
+// last_only: instead of out [B,T,H], `dst_host` receives pred [B,H] = out[:, T-1, :] * (vmax - vmin) + vmin
+int host_pipeline(const float* adj, const float* x_host, const float* w1, const float* b1, const float* w2,
+                  const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                  float* dst_host, int64_t B, int T, int S, int F_in, int F_hid, int F_out, int H, int64_t chunk,
+                  int flags, void* workspace, size_t workspace_bytes, int device, bool last_only, double vmin,
+                  double vmax) {
     Plan p;
     if (chunk == 0) chunk = kHostDefaultChunk;
     int rc = make_plan(p, B, T, S, F_in, F_hid, F_out, H, chunk, false, flags);
     if (rc) return rc;
     if (B == 0) return WG_OK;
-    if (any_null({adj, x_host, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, out_host}))
+    if (any_null({adj, x_host, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, dst_host}))
         return fail(WG_ERR_BAD_ARG, "null pointer argument");
     const size_t xs = align_up((size_t)p.chunk * T * S * F_in * 4);
     const size_t os = align_up((size_t)p.chunk * T * H * 4);
+    const size_t ps = align_up((size_t)p.chunk * H * 4);
     const size_t wsz = align_up(p.total);
-    const size_t need = kHostLanes * wsz + kHostSlots * (xs + os);
+    const size_t need = kHostLanes * wsz + kHostSlots * (xs + os + ps);
     if (!workspace || reinterpret_cast<uintptr_t>(workspace) % kAlign)
         return fail(WG_ERR_WORKSPACE, "workspace NULL or not %zu-byte aligned", kAlign);
     if (workspace_bytes < need)
         return fail(WG_ERR_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
     DeviceGuard g(device);
     WG_CUDA(g.err);
+    HostCtx* cx = nullptr;
+    if ((rc = host_ctx(device, &cx))) return rc;
 
     char* base = static_cast<char*>(workspace);
     void* lane_ws[kHostLanes];
     for (int l = 0; l < kHostLanes; ++l) lane_ws[l] = base + l * wsz;
     float* xdev[kHostSlots];
     float* odev[kHostSlots];
+    float* pdev[kHostSlots];
     for (int i = 0; i < kHostSlots; ++i) {
         xdev[i] = reinterpret_cast<float*>(base + kHostLanes * wsz + i * xs);
         odev[i] = reinterpret_cast<float*>(base + kHostLanes * wsz + kHostSlots * xs + i * os);
+        pdev[i] = reinterpret_cast<float*>(base + kHostLanes * wsz + kHostSlots * (xs + os) + i * ps);
     }
-
-    cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[kHostLanes] = {};
-    cudaEvent_t ev_in[kHostSlots] = {}, ev_cmp[kHostSlots] = {}, ev_out[kHostSlots] = {};
     int result = WG_OK;
-    auto cleanup = [&]() {
-        for (int i = 0; i < kHostSlots; ++i) {
-            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
-            if (ev_cmp[i]) cudaEventDestroy(ev_cmp[i]);
-            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
-        }
-        if (s_in) cudaStreamDestroy(s_in);
-        if (s_out) cudaStreamDestroy(s_out);
-        for (int l = 0; l < kHostLanes; ++l)
-            if (s_cmp[l]) cudaStreamDestroy(s_cmp[l]);
-    };
 #define WG_CUDA_H(expr)                                                                         \
     do {                                                                                        \
         cudaError_t e_ = (expr);                                                                \
@@ -930,24 +955,14 @@ int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const flo
             result = fail(WG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),  \
                           __FILE__, __LINE__);                                                  \
             cudaDeviceSynchronize();                                                            \
-            cleanup();                                                                          \
             return result;                                                                      \
         }                                                                                       \
     } while (0)
 
-    WG_CUDA_H(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    WG_CUDA_H(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    for (int l = 0; l < kHostLanes; ++l) WG_CUDA_H(cudaStreamCreateWithFlags(&s_cmp[l], cudaStreamNonBlocking));
-    for (int i = 0; i < kHostSlots; ++i) {
-        WG_CUDA_H(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-        WG_CUDA_H(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming));
-        WG_CUDA_H(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-    }
     const long long n_chunks = (B + p.chunk - 1) / p.chunk;
     for (int l = 0; l < kHostLanes && l < n_chunks; ++l) {   // each lane packs the parameters into its own scratch
-        if ((rc = launch_pack(p, lane_ws[l], w_ih, w_hh, b_ih, b_hh, s_cmp[l]))) {
+        if ((rc = launch_pack(p, lane_ws[l], w_ih, w_hh, b_ih, b_hh, cx->s_cmp[l]))) {
             cudaDeviceSynchronize();
-            cleanup();
             return rc;
         }
     }
@@ -957,31 +972,61 @@ int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const flo
         const long long b0 = c * p.chunk;
         const long long Bc = (B - b0) < p.chunk ? (B - b0) : p.chunk;
         // x staging slot is free once the compute that read it (chunk c - slots) is done
-        if (c >= kHostSlots) WG_CUDA_H(cudaStreamWaitEvent(s_in, ev_cmp[sl], 0));
+        if (c >= kHostSlots) WG_CUDA_H(cudaStreamWaitEvent(cx->s_in, cx->ev_cmp[sl], 0));
         WG_CUDA_H(cudaMemcpyAsync(xdev[sl], x_host + (size_t)b0 * x_seq, (size_t)Bc * x_seq * 4,
-                                  cudaMemcpyHostToDevice, s_in));
-        WG_CUDA_H(cudaEventRecord(ev_in[sl], s_in));
+                                  cudaMemcpyHostToDevice, cx->s_in));
+        WG_CUDA_H(cudaEventRecord(cx->ev_in[sl], cx->s_in));
         // compute waits for its input and for the D2H that last used this out slot (chunk c - slots);
         // the lane's scratch is free because chunk c - lanes ran on the same stream
-        WG_CUDA_H(cudaStreamWaitEvent(s_cmp[lane], ev_in[sl], 0));
-        if (c >= kHostSlots) WG_CUDA_H(cudaStreamWaitEvent(s_cmp[lane], ev_out[sl], 0));
-        if ((rc = run_chunk(p, lane_ws[lane], adj, xdev[sl], w1, b1, w2, b2, odev[sl], Bc, s_cmp[lane]))) {
+        WG_CUDA_H(cudaStreamWaitEvent(cx->s_cmp[lane], cx->ev_in[sl], 0));
+        if (c >= kHostSlots) WG_CUDA_H(cudaStreamWaitEvent(cx->s_cmp[lane], cx->ev_out[sl], 0));
+        if ((rc = run_chunk(p, lane_ws[lane], adj, xdev[sl], w1, b1, w2, b2, odev[sl], Bc, cx->s_cmp[lane]))) {
             cudaDeviceSynchronize();
-            cleanup();
             return rc;
         }
-        WG_CUDA_H(cudaEventRecord(ev_cmp[sl], s_cmp[lane]));
-        WG_CUDA_H(cudaStreamWaitEvent(s_out, ev_cmp[sl], 0));
-        WG_CUDA_H(cudaMemcpyAsync(out_host + (size_t)b0 * o_seq, odev[sl], (size_t)Bc * o_seq * 4,
-                                  cudaMemcpyDeviceToHost, s_out));
-        WG_CUDA_H(cudaEventRecord(ev_out[sl], s_out));
+        if (last_only) {   // only 3S floats per window leave the GPU (src/main.py:103,116)
+            if ((rc = wg_denorm_last_step_f32(odev[sl], pdev[sl], Bc, T, H, vmin, vmax, device, cx->s_cmp[lane]))) {
+                cudaDeviceSynchronize();
+                return rc;
+            }
+        }
+        WG_CUDA_H(cudaEventRecord(cx->ev_cmp[sl], cx->s_cmp[lane]));
+        WG_CUDA_H(cudaStreamWaitEvent(cx->s_out, cx->ev_cmp[sl], 0));
+        if (last_only)
+            WG_CUDA_H(cudaMemcpyAsync(dst_host + (size_t)b0 * H, pdev[sl], (size_t)Bc * H * 4, cudaMemcpyDeviceToHost,
+                                      cx->s_out));
+        else
+            WG_CUDA_H(cudaMemcpyAsync(dst_host + (size_t)b0 * o_seq, odev[sl], (size_t)Bc * o_seq * 4,
+                                      cudaMemcpyDeviceToHost, cx->s_out));
+        WG_CUDA_H(cudaEventRecord(cx->ev_out[sl], cx->s_out));
     }
-    WG_CUDA_H(cudaStreamSynchronize(s_out));
-    for (int l = 0; l < kHostLanes; ++l) WG_CUDA_H(cudaStreamSynchronize(s_cmp[l]));
-    WG_CUDA_H(cudaStreamSynchronize(s_in));
+    WG_CUDA_H(cudaStreamSynchronize(cx->s_out));
+    for (int l = 0; l < kHostLanes; ++l) WG_CUDA_H(cudaStreamSynchronize(cx->s_cmp[l]));
+    WG_CUDA_H(cudaStreamSynchronize(cx->s_in));
 #undef WG_CUDA_H
-    cleanup();
     return WG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wg_gcn_gru_forward_host_f32(const float* adj, const float* x_host, const float* w1, const float* b1,
+                                const float* w2, const float* b2, const float* w_ih, const float* w_hh,
+                                const float* b_ih, const float* b_hh, float* out_host, int64_t B, int T,
+                                int S, int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags,
+                                void* workspace, size_t workspace_bytes, int device) {
+    return host_pipeline(adj, x_host, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, out_host, B, T, S, F_in, F_hid, F_out, H,
+                         chunk, flags, workspace, workspace_bytes, device, false, 0.0, 1.0);
+}
+
+int wg_gcn_gru_predict_host_f32(const float* adj, const float* x_host, const float* w1, const float* b1,
+                                const float* w2, const float* b2, const float* w_ih, const float* w_hh,
+                                const float* b_ih, const float* b_hh, float* pred_host, int64_t B, int T,
+                                int S, int F_in, int F_hid, int F_out, int H, int64_t chunk, int flags, double vmin,
+                                double vmax, void* workspace, size_t workspace_bytes, int device) {
+    return host_pipeline(adj, x_host, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, pred_host, B, T, S, F_in, F_hid, F_out,
+                         H, chunk, flags, workspace, workspace_bytes, device, true, vmin, vmax);
 }
 
 int wg_gcn_layer_f32(const float* adj, const float* attr, const float* weight, const float* bias,

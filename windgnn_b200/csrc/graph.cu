@@ -120,6 +120,100 @@ __global__ void normalise_kernel(const double* __restrict__ A, const double* __r
     }
 }
 
+
+// ---- CSR output of the kNN graph: no S x S matrix anywhere (2 MB of pattern bits at S = 4096) ----
+// The values are bit-identical to the dense path: a column sum that skips the exact zeros of the dense
+// matrix is the same sequence of additions (x + 0.0 == x), the pattern is symmetric and a_ij == a_ji
+// bit for bit (X and -X square to the same double), so d_j is row j's entries added in ascending column order.
+__global__ void bits_scatter_kernel(const int* __restrict__ nbr, unsigned* __restrict__ bits, int S, int k, int W) {
+    const long long n = (long long)S * (k + 1);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / (k + 1)), r = (int)(e % (k + 1));
+        const int j = r == k ? i : nbr[(size_t)i * k + r];      // r == k: the self loop
+        if (j >= 0 && j < S) {
+            atomicOr(bits + (size_t)i * W + (j >> 5), 1u << (j & 31));
+            atomicOr(bits + (size_t)j * W + (i >> 5), 1u << (i & 31));
+        }
+    }
+}
+__global__ void row_count_kernel(const unsigned* __restrict__ bits, int* __restrict__ cnt, int S, int W) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= S) return;
+    int c = 0;
+    for (int w = lane; w < W; w += 32) c += __popc(bits[(size_t)warp * W + w]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cnt[warp] = c;
+}
+// exclusive scan of cnt[0..S) into rowptr[0..S]; one block (S is a station count)
+__global__ void row_scan_kernel(const int* __restrict__ cnt, int* __restrict__ rowptr, int S) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x, n = blockDim.x;
+    const int per = (S + n - 1) / n, lo = t * per, hi = lo + per < S ? lo + per : S;
+    long long s = 0;
+    for (int i = lo; i < hi; ++i) s += cnt[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        long long run = 0;
+        for (int i = 0; i < n; ++i) { const long long v = part[i]; part[i] = run; run += v; }
+    }
+    __syncthreads();
+    long long run = part[t];
+    for (int i = lo; i < hi; ++i) { rowptr[i] = (int)run; run += cnt[i]; }
+    if (t == n - 1) rowptr[S] = (int)run;   // threads past S have lo >= S: run == total for the last thread
+}
+// one warp per row: columns ascending, a_ij; lane 0 then adds the row in order -> dh_i
+__global__ void csr_fill_kernel(const double* __restrict__ xy, const unsigned* __restrict__ bits,
+                                const int* __restrict__ rowptr, int* __restrict__ colidx, double* __restrict__ aval,
+                                double* __restrict__ dh, int S, int W, long long capacity) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= S) return;
+    const int e0 = rowptr[i], e1 = rowptr[i + 1];
+    if ((long long)e1 > capacity) return;   // the caller's buffers are too small: reported by the host
+    int e = e0;
+    for (int w0 = 0; w0 < W; w0 += 32) {
+        const int w = w0 + lane;
+        const unsigned b = w < W ? bits[(size_t)i * W + w] : 0u;
+        const int c = __popc(b);
+        int pre = c;   // inclusive scan of the counts over the lanes
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += v;
+        }
+        int pos = e + pre - c;
+        unsigned bb = b;
+        while (bb) {
+            const int bit = __ffs(bb) - 1;
+            bb &= bb - 1;
+            const int j = (w << 5) + bit;
+            colidx[pos] = j;
+            aval[pos] = (j == i) ? 1.0 : 1.0 / sqrt(edge_key(xy, i, j));
+            ++pos;
+        }
+        e += __shfl_sync(0xffffffffu, pre, 31);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double d = 0.0;
+        for (int q = e0; q < e1; ++q) d = d + aval[q];
+        dh[i] = (1.0 / d) * sqrt(d);
+    }
+}
+__global__ void csr_normalise_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                     const double* __restrict__ aval, const double* __restrict__ dh,
+                                     double* __restrict__ v64, float* __restrict__ v32, int S, long long capacity) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= S) return;
+    const int e0 = rowptr[i], e1 = rowptr[i + 1];
+    if ((long long)e1 > capacity) return;
+    for (int e = e0 + lane; e < e1; e += 32) {
+        const double v = (dh[i] * aval[e]) * dh[colidx[e]];
+        if (v64) v64[e] = v;
+        if (v32) v32[e] = (float)v;
+    }
+}
+
 __device__ __forceinline__ unsigned long long splitmix64_nth(unsigned long long seed, unsigned long long n) {
     unsigned long long z = seed + n * 0x9E3779B97F4A7C15ULL;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -192,6 +286,62 @@ int wg_build_graph_f64(const double* xy, double* adj_f64, float* adj_f32, int S,
     if (e != cudaSuccess) {
         char buf[256];
         snprintf(buf, sizeof(buf), "build_graph: %s", cudaGetErrorString(e));
+        return wg_internal_fail(WG_ERR_CUDA, buf);
+    }
+    return WG_OK;
+}
+
+
+size_t wg_build_graph_csr_workspace_bytes(int S, int k) {
+    if (S <= 0 || k <= 0) return 0;
+    const int kk = k > S - 1 ? S - 1 : k;
+    const size_t W = (size_t)(S + 31) / 32;
+    // neighbour lists, pattern bits, row counts, a_ij per stored entry (capacity S (2k + 1)), dh
+    return al((size_t)S * kk * 4) + al((size_t)S * W * 4) + al((size_t)S * 4) + al((size_t)S * (2 * kk + 1) * 8) +
+           al((size_t)S * 8);
+}
+
+int wg_build_graph_csr_f64(const double* xy, int S, int k, int32_t* rowptr, int32_t* colidx, double* vals_f64,
+                           float* vals_f32, int64_t capacity, void* workspace, size_t workspace_bytes, int device,
+                           void* stream) {
+    if (S <= 0 || k <= 0) return wg_internal_fail(WG_ERR_BAD_ARG, "build_graph_csr: S and k must be > 0");
+    if (!xy || !rowptr || !colidx || (!vals_f64 && !vals_f32))
+        return wg_internal_fail(WG_ERR_BAD_ARG, "build_graph_csr: null pointer");
+    const int kk = k > S - 1 ? S - 1 : k;
+    if (capacity < (int64_t)S * (2 * kk + 1))
+        return wg_internal_fail(WG_ERR_BAD_ARG, "build_graph_csr: capacity must be at least S * (2k + 1) entries");
+    const size_t need = wg_build_graph_csr_workspace_bytes(S, k);
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255))
+        return wg_internal_fail(WG_ERR_WORKSPACE, "build_graph_csr: workspace NULL, misaligned or too small");
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess || (prev != device && cudaSetDevice(device) != cudaSuccess))
+        return wg_internal_fail(WG_ERR_CUDA, "build_graph_csr: cannot select CUDA device");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int W = (S + 31) / 32;
+    char* base = static_cast<char*>(workspace);
+    int* nbr = reinterpret_cast<int*>(base);                     base += al((size_t)S * kk * 4);
+    unsigned* bits = reinterpret_cast<unsigned*>(base);          base += al((size_t)S * W * 4);
+    int* cnt = reinterpret_cast<int*>(base);                     base += al((size_t)S * 4);
+    double* aval = reinterpret_cast<double*>(base);              base += al((size_t)S * (2 * kk + 1) * 8);
+    double* dh = reinterpret_cast<double*>(base);
+    const int threads = 256;
+    const int warp_blocks = (int)(((long long)S * 32 + threads - 1) / threads);
+    cudaMemsetAsync(bits, 0, (size_t)S * W * 4, st);
+    knn_kernel<<<warp_blocks, threads, 0, st>>>(xy, nbr, S, kk);
+    const long long ne = (long long)S * (kk + 1);
+    int b2 = (int)((ne + threads - 1) / threads);
+    if (b2 > 148 * 16) b2 = 148 * 16;
+    bits_scatter_kernel<<<b2, threads, 0, st>>>(nbr, bits, S, kk, W);
+    row_count_kernel<<<warp_blocks, threads, 0, st>>>(bits, cnt, S, W);
+    row_scan_kernel<<<1, 1024, 0, st>>>(cnt, rowptr, S);
+    csr_fill_kernel<<<warp_blocks, threads, 0, st>>>(xy, bits, rowptr, colidx, aval, dh, S, W, (long long)capacity);
+    csr_normalise_kernel<<<warp_blocks, threads, 0, st>>>(rowptr, colidx, aval, dh, vals_f64, vals_f32, S,
+                                                          (long long)capacity);
+    cudaError_t e = cudaGetLastError();
+    if (prev != device) cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "build_graph_csr: %s", cudaGetErrorString(e));
         return wg_internal_fail(WG_ERR_CUDA, buf);
     }
     return WG_OK;

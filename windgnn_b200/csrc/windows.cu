@@ -78,6 +78,45 @@ struct DevGuard {
     }
 };
 
+
+// Pivot of the long table (src/step4_sequence_preparer.py:36-47): the reference walks the stations in
+// np.unique order and stacks each station's rows, in file order, along a new station axis:
+//   table[t][s][:] = values of the t-th row (file order) whose station is s.
+// One CTA per station scans the station-id column once; a row's time index is the number of earlier
+// rows of the same station (block-wide exclusive prefix count of the match flags).
+__global__ void __launch_bounds__(256) pivot_kernel(const int* __restrict__ station, const float* __restrict__ values,
+                                                    float* __restrict__ table, int* __restrict__ counts,
+                                                    long long n_rows, int S, int F, long long Ttot) {
+    __shared__ int warp_sum[8];
+    __shared__ int running;
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (long long base = 0; base < n_rows; base += 256) {
+        const long long i = base + tid;
+        const bool hit = i < n_rows && station[i] == s;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_sum[warp] = __popc(m);
+        __syncthreads();
+        int before = running;
+        for (int w = 0; w < warp; ++w) before += warp_sum[w];
+        const long long t = before + __popc(m & ((1u << lane) - 1u));
+        if (hit && t < Ttot) {
+            const float* src = values + i * F;
+            float* dst = table + (t * S + s) * F;
+            for (int f = 0; f < F; ++f) dst[f] = __ldg(src + f);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += warp_sum[w];
+            running += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) counts[s] = running;
+}
+
 }  // namespace
 
 extern "C" {
@@ -124,6 +163,22 @@ int wg_denorm_last_step_f32(const float* out, float* pred, int64_t B, int T, int
     const float scale = (float)(vmax - vmin), lo = (float)vmin;
     denorm_last_kernel<<<grid_for(B * H), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, pred, B, T, H, scale, lo);
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return wg_internal_fail(WG_ERR_CUDA, cudaGetErrorString(e));
+    return WG_OK;
+}
+
+
+int wg_pivot_table_f32(const int32_t* station, const float* values, float* table, int32_t* counts, int64_t n_rows,
+                       int S, int F, int64_t Ttot, int device, void* stream) {
+    if (n_rows < 0 || S <= 0 || F <= 0 || Ttot < 0) return wg_internal_fail(WG_ERR_BAD_ARG, "pivot: bad dimension");
+    if (!counts || (n_rows > 0 && (!station || !values)) || (Ttot > 0 && !table))
+        return wg_internal_fail(WG_ERR_BAD_ARG, "pivot: null pointer");
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess || (prev != device && cudaSetDevice(device) != cudaSuccess))
+        return wg_internal_fail(WG_ERR_CUDA, "pivot: cannot select CUDA device");
+    pivot_kernel<<<S, 256, 0, static_cast<cudaStream_t>(stream)>>>(station, values, table, counts, n_rows, S, F, Ttot);
+    cudaError_t e = cudaGetLastError();
+    if (prev != device) cudaSetDevice(prev);
     if (e != cudaSuccess) return wg_internal_fail(WG_ERR_CUDA, cudaGetErrorString(e));
     return WG_OK;
 }

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .graph import CsrGraph
 
 
 class _InferenceOnly(torch.autograd.Function):
@@ -89,24 +90,30 @@ class GCN_GRU(nn.Module):
         )
         widths = (self.conv1.weight.shape[0], self.conv1.weight.shape[1], self.conv2.weight.shape[1])
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        if torch.is_grad_enabled() and (attr_matrix.requires_grad or adj_matrix.requires_grad):
+        is_csr = isinstance(adj_matrix, CsrGraph)
+        if torch.is_grad_enabled() and (attr_matrix.requires_grad or (not is_csr and adj_matrix.requires_grad)):
             # the reference never differentiates w.r.t. its data (main.py:66-77); the library has no such gradient
             raise RuntimeError("windgnn_b200.GCN_GRU: gradients w.r.t. attr_matrix / adj_matrix are not implemented")
-        if adj_matrix.shape[0] > self.DENSE_MAX_STATIONS or max(widths) > 16:
-            key = (adj_matrix.data_ptr(), adj_matrix._version, tuple(adj_matrix.shape))
-            if self._csr_cache is None or self._csr_cache[0] != key:
-                self._csr_cache = (key, ops.dense_to_csr(adj_matrix))
+        if is_csr or adj_matrix.shape[0] > self.DENSE_MAX_STATIONS or max(widths) > 16:
+            # scaled shapes (thousands of stations, wide hidden layer): CSR adjacency path
+            if is_csr:
+                csr = (adj_matrix.rowptr, adj_matrix.colidx, adj_matrix.vals)
+            else:
+                key = (adj_matrix.data_ptr(), adj_matrix._version, tuple(adj_matrix.shape))
+                if self._csr_cache is None or self._csr_cache[0] != key:
+                    self._csr_cache = (key, ops.dense_to_csr(adj_matrix))
+                csr = self._csr_cache[1]
             if needs_grad:
                 # forward works under grad mode (main.py:66 style calls); backward() explains the limit
                 out = _InferenceOnly.apply(
                     "windgnn_b200.GCN_GRU: training is implemented for dense graphs with at most "
                     f"{self.DENSE_MAX_STATIONS} stations and GCN widths <= 16 (got {adj_matrix.shape[0]} stations, "
                     f"widths {widths}); the scaled shapes are inference-only",
-                    lambda: ops.gcn_gru_forward_csr(*self._csr_cache[1], attr_matrix, *[p.detach() for p in params],
-                                                    self.chunk),
+                    lambda: ops.gcn_gru_forward_csr(*csr, attr_matrix, *[p.detach() for p in params], self.chunk,
+                                                    self._flags()),
                     *params)
             else:
-                out = ops.gcn_gru_forward_csr(*self._csr_cache[1], attr_matrix, *params, self.chunk)
+                out = ops.gcn_gru_forward_csr(*csr, attr_matrix, *params, self.chunk, self._flags())
         elif needs_grad:
             # training (main.py:66 runs with grad enabled): forward that saves the gate values, library
             # backward (train.py); FP32 path only
@@ -118,14 +125,16 @@ class GCN_GRU(nn.Module):
         return out.squeeze(0)  # step6:26 — a no-op unless B == 1
 
     @torch.no_grad()
-    def forward_host(self, adj_matrix, attr_host, out_host=None):
-        """Host-buffer end-to-end forward (H2D, compute, D2H overlapped chunk by chunk)."""
+    def forward_host(self, adj_matrix, attr_host, out_host=None, last_step_range=None):
+        """Host-buffer end-to-end forward (H2D, compute, D2H overlapped chunk by chunk).  With
+        ``last_step_range=(wind_min, wind_max)`` only the de-normalised last timestep ``[B, 3S]`` comes back
+        (the evaluation of main.py:101-116 in one call)."""
         params = (
             self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
             self.gru.weight_ih_l0, self.gru.weight_hh_l0, self.gru.bias_ih_l0, self.gru.bias_hh_l0,
         )
         return ops.gcn_gru_forward_host(adj_matrix, attr_host, [p.detach() for p in params], out_host, self.chunk,
-                                        flags=self._flags())
+                                        flags=self._flags(), last_step_range=last_step_range)
 
     def _flags(self) -> int:
         from . import _lib

@@ -150,9 +150,11 @@ def gcn_gru_forward_csr(
     b_ih: torch.Tensor,
     b_hh: torch.Tensor,
     chunk: int = 0,
+    flags: int = 0,
 ) -> torch.Tensor:
     """The same forward with the adjacency in CSR form (int32 ``rowptr [S+1]``, ``colidx [nnz]``,
-    fp32 ``vals [nnz]``): the large-sparse-graph path (thousands of stations, wide GCN hidden layer)."""
+    fp32 ``vals [nnz]``): the large-sparse-graph path (thousands of stations, wide GCN hidden layer).
+    ``flags``: as for ``gcn_gru_forward`` (the tensor path serves the projection and the recurrence)."""
     lib = _lib.load()
     x = _require_cuda_f32("attr_matrix", x)
     dev = x.device
@@ -178,23 +180,25 @@ def gcn_gru_forward_csr(
     out = torch.empty((B, T, H), dtype=torch.float32, device=dev)
     if B == 0 or T == 0:
         return out
-    nbytes = lib.wg_gcn_gru_csr_workspace_bytes(B, T, S, F_in, F_hid, F_out, H, chunk)
+    nbytes = lib.wg_gcn_gru_csr_workspace_bytes(B, T, S, F_in, F_hid, F_out, H, chunk, flags)
     if nbytes == 0:
-        raise _lib.WindGNNError(_lib.WG_ERR_BAD_ARG, _lib.last_error())
+        raise _lib.WindGNNError(_lib.WG_ERR_UNSUPPORTED if "tensor-core" in _lib.last_error() else _lib.WG_ERR_BAD_ARG,
+                                _lib.last_error())
     ws = _workspace(dev, nbytes)
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(
         lib.wg_gcn_gru_forward_csr_f32(
             rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(), x.data_ptr(), w1.data_ptr(), b1.data_ptr(),
             w2.data_ptr(), b2.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
-            out.data_ptr(), B, T, S, F_in, F_hid, F_out, H, chunk, ws.data_ptr(), ws.numel(), dev.index or 0, stream,
+            out.data_ptr(), B, T, S, F_in, F_hid, F_out, H, chunk, flags, ws.data_ptr(), ws.numel(), dev.index or 0,
+            stream,
         )
     )
     return out
 
 
 @gcn_gru_forward_csr.register_fake
-def _(rowptr, colidx, vals, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, chunk=0):
+def _(rowptr, colidx, vals, x, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh, chunk=0, flags=0):
     return x.new_empty((x.shape[0], x.shape[1], w_hh.shape[1]))
 
 
@@ -241,10 +245,14 @@ def _(adj, attr, weight, bias):
     return attr.new_empty((*attr.shape[:-1], weight.shape[1]))
 
 
-def gcn_gru_forward_host(adj, x_host, params, out_host=None, chunk: int = 0, device=None, flags: int = 0):
+def gcn_gru_forward_host(adj, x_host, params, out_host=None, chunk: int = 0, device=None, flags: int = 0,
+                         last_step_range=None):
     """End-to-end variant: ``x_host`` / ``out_host`` are HOST tensors (pin them for full
     copy/compute overlap); the batch is streamed through the GPU in chunks.  Blocks until
-    ``out_host`` is complete.  ``params`` = the 8 tensors in state_dict order, on the GPU."""
+    ``out_host`` is complete.  ``params`` = the 8 tensors in state_dict order, on the GPU.
+
+    ``last_step_range=(wind_min, wind_max)``: only the last timestep of every window, de-normalised
+    (what the reference's evaluation reads, main.py:103,116), comes back: ``out_host`` is ``[B, H]``."""
     lib = _lib.load()
     if x_host.is_cuda or x_host.dtype != torch.float32 or not x_host.is_contiguous():
         raise RuntimeError("x_host must be a contiguous float32 CPU tensor")
@@ -252,10 +260,11 @@ def gcn_gru_forward_host(adj, x_host, params, out_host=None, chunk: int = 0, dev
     dev = adj.device if device is None else torch.device(device)
     w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh = (_require_cuda_f32(f"param{i}", t, dev) for i, t in enumerate(params))
     B, T, S, F_in, F_hid, F_out, H = _dims(adj, x_host, w1, b1, w2, b2, w_ih, w_hh, b_ih, b_hh)
+    shape = (B, H) if last_step_range is not None else (B, T, H)
     if out_host is None:
-        out_host = torch.empty((B, T, H), dtype=torch.float32, pin_memory=True)
-    if out_host.is_cuda or out_host.dtype != torch.float32 or not out_host.is_contiguous() or out_host.shape != (B, T, H):
-        raise RuntimeError("out_host must be a contiguous float32 CPU tensor [B, T, H]")
+        out_host = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    if out_host.is_cuda or out_host.dtype != torch.float32 or not out_host.is_contiguous() or out_host.shape != shape:
+        raise RuntimeError(f"out_host must be a contiguous float32 CPU tensor {list(shape)}")
     if B == 0:
         return out_host
     nbytes = lib.wg_gcn_gru_host_workspace_bytes(B, T, S, F_in, F_hid, F_out, H, chunk, flags)
@@ -263,11 +272,13 @@ def gcn_gru_forward_host(adj, x_host, params, out_host=None, chunk: int = 0, dev
         raise _lib.WindGNNError(_lib.WG_ERR_BAD_ARG, _lib.last_error())
     ws = _workspace(dev, nbytes, "host")
     torch.cuda.current_stream(dev).synchronize()  # parameters / adj may have been produced on it
-    _lib.check(
-        lib.wg_gcn_gru_forward_host_f32(
-            adj.data_ptr(), x_host.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
-            w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), out_host.data_ptr(),
-            B, T, S, F_in, F_hid, F_out, H, chunk, flags, ws.data_ptr(), ws.numel(), dev.index or 0,
-        )
-    )
+    ptrs = (adj.data_ptr(), x_host.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+            w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), out_host.data_ptr())
+    if last_step_range is None:
+        _lib.check(lib.wg_gcn_gru_forward_host_f32(*ptrs, B, T, S, F_in, F_hid, F_out, H, chunk, flags, ws.data_ptr(),
+                                                   ws.numel(), dev.index or 0))
+    else:
+        _lib.check(lib.wg_gcn_gru_predict_host_f32(*ptrs, B, T, S, F_in, F_hid, F_out, H, chunk, flags,
+                                                   float(last_step_range[0]), float(last_step_range[1]),
+                                                   ws.data_ptr(), ws.numel(), dev.index or 0))
     return out_host

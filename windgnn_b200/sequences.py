@@ -29,6 +29,42 @@ def num_windows(n_rows: int, seq_length: int = SEQ_LENGTH, horizons: int = HORIZ
     return int(_lib.load().wg_num_windows(n_rows, seq_length, horizons))
 
 
+def pivot_long_table(station_names, values: torch.Tensor):
+    """Long table -> ``[time, station, feature]`` like step4:36-47.
+
+    ``station_names``: one name per row of the long table (column 0 of the reference's array), any
+    sequence NumPy can ``np.unique``; ``values [n_rows, F]`` the numeric columns (2:15) on the GPU, file
+    order.  Stations end up in ``np.unique`` (alphabetical) order, each station's rows keep their file
+    order.  Returns ``(table [Ttot, S, F], station_order)``.  The name -> rank map is host plumbing
+    (strings); the data movement is the library's ``wg_pivot_table_f32``."""
+    import numpy as np
+
+    lib = _lib.load()
+    values = _cuda_f32("values", values)
+    if values.dim() != 2:
+        raise RuntimeError("values must be [n_rows, F]")
+    n_rows, F = values.shape
+    stations, inverse = np.unique(np.asarray(station_names), return_inverse=True)   # step4:38
+    if inverse.shape[0] != n_rows:
+        raise RuntimeError(f"{inverse.shape[0]} station names for {n_rows} rows")
+    S = len(stations)
+    if S == 0 or n_rows % S:
+        raise RuntimeError(f"{n_rows} rows do not split evenly over {S} stations (the reference's np.concatenate "
+                           "along the station axis needs equal counts, step4:47)")
+    Ttot = n_rows // S
+    dev = values.device
+    sid = torch.from_numpy(inverse.astype(np.int32)).to(dev)
+    table = torch.empty((Ttot, S, F), dtype=torch.float32, device=dev)
+    counts = torch.empty(S, dtype=torch.int32, device=dev)
+    _lib.check(lib.wg_pivot_table_f32(sid.data_ptr(), values.data_ptr(), table.data_ptr(), counts.data_ptr(), n_rows, S,
+                                      F, Ttot, dev.index or 0, torch.cuda.current_stream(dev).cuda_stream))
+    c = counts.cpu()
+    if int(c.min()) != Ttot or int(c.max()) != Ttot:
+        raise RuntimeError(f"stations have unequal row counts ({int(c.min())} .. {int(c.max())}); the reference's "
+                           "pivot (step4:47) requires them equal")
+    return table, list(stations)
+
+
 def create_sequences(table: torch.Tensor, seq_length: int = SEQ_LENGTH, perm: torch.Tensor | None = None,
                      label_feature: int = LABEL_FEATURE, horizons: int = HORIZONS, want_x: bool = True):
     """``table [Ttot, S, F]`` -> ``(x [N, L, S, F], y [N, L, horizons*S])`` like step4:7-22.
