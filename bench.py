@@ -354,13 +354,14 @@ def scaled_leg(ctx: Ctx, which: str, steps: int, warmup: int, lib_peak: float, b
             model.conv1.weight.mul_(0.05)
             model.conv2.weight.mul_(0.05)
         ll = windgnn_b200.synthetic_coordinates(S4, seed=0, device=dev).cpu().numpy()
-        adj = windgnn_b200.knn_graph_from_latlon(ll, k=8, device=dev)
-        nnz = int((adj != 0).sum().item())
+        adj = windgnn_b200.knn_graph_csr_from_latlon(ll, k=8, device=dev)   # CSR straight from the kNN builder
+        nnz = adj.nnz
         x = torch.rand((B4, T4, S4, F), generator=gen, device=dev)
         Sx, Tx, scaling, units = S4, T4, "weak", world * B4
         fl, by = flop_per_seq(S4, T4, F, Fh4, F, H4, nnz=nnz), bytes_per_seq(S4, T4, F, H4)
-        name = (f"synthetic 4096-station kNN(k=8) graph (nnz {nnz}), GCN_GRU(13,128,13,53248,128), T=24, "
-                f"{B4} windows per GPU (BASELINE.json configs[3], SURVEY 8(d) variant C)")
+        name = (f"synthetic 4096-station kNN(k=8) graph (nnz {nnz}, CSR from the GPU builder), "
+                f"GCN_GRU(13,128,13,53248,128), T=24, {B4} windows per GPU (BASELINE.json configs[3], SURVEY 8(d) "
+                "variant C)")
 
         def step():
             model(adj, x)
@@ -369,10 +370,20 @@ def scaled_leg(ctx: Ctx, which: str, steps: int, warmup: int, lib_peak: float, b
         ms = timed_events(ctx, step, steps, warmup)
     value = units * steps / (ms * 1e-3)
     tfl = fl * value / world / 1e12
+    tensor = None
+    if which == "fwd4096":   # the same configuration on the tensor path (projection + recurrence on tcgen05)
+        model.precision = "tensor"
+        with torch.no_grad():
+            ms_t = timed_events(ctx, step, steps, warmup)
+        model.precision = "fp32"
+        tensor = {"value": units * steps / (ms_t * 1e-3), "ms_per_step": ms_t / steps,
+                  "precision": "tensor (tcgen05 projection and recurrence, split fp16 operands); the CSR GCN stays FP32"}
     out = {"workload": name, "value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
            "scaling": scaling, "S": Sx, "T": Tx, "station_sequence_predictions_per_s": value * Sx,
            "tflops_per_gpu": tfl, "frac_fp32": tfl / lib_peak if lib_peak > 0 else None,
            "hbm_gbs_algorithmic_per_gpu": by * value / world / 1e9, "flop_per_seq": fl}
+    if tensor is not None:
+        out["tensor_path"] = tensor
     del x, model, adj
     torch.cuda.empty_cache()
     return out
@@ -427,8 +438,8 @@ def main():
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-scaled", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3"],
-                    help="fp32: every contraction as FP32 FMA; tf32x3: tensor-core path (tcgen05, error-compensated)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tensor", "tf32x3"],
+                    help="fp32: every contraction as FP32 FMA; tensor: projection and recurrence on tcgen05 (split fp16 operands)")
     ap.add_argument("--ref-seqs", type=int, default=B_PER_GPU,
                     help="sequences per step of the reference arm (default: the full configs[1] step)")
     ap.add_argument("--workload", default="fwd34", choices=["fwd34", "fwd34_1m", "fwd4096", "fwd7"],
@@ -520,7 +531,7 @@ def main():
     # ---------------- the opt-in tensor-core path, same workload, same timing rules ----------------
     tensor_path = None
     if args.precision == "fp32" and not args.no_tensor_path:
-        model.precision = "tf32x3"
+        model.precision = "tensor"
         try:
             with torch.no_grad():
                 def tc_step():
@@ -703,8 +714,20 @@ def main():
                    "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "pipeline_chunk": 256, "compute_lanes": 2,
                    "timing": "host wall clock around the blocking calls (the public API returns when the host output "
                              "buffer is complete), max over ranks"}
+            # what the reference's evaluation loop needs (main.py:101-116): de-normalised last step only
+            ph = torch.empty((Bg, H), dtype=torch.float32, pin_memory=True)
+            ctx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(max(3, e2e_steps // 4)):
+                model.forward_host(adj, xh, ph, last_step_range=(0.0, 83.6))
+            torch.cuda.synchronize(dev)
+            dtp = ctx.max_over_ranks(time.perf_counter() - t0) / max(3, e2e_steps // 4)
+            e2e["last_step_only"] = {"value": world * Bg / dtp, "ms_per_step": 1e3 * dtp, "d2h_bytes_per_step": Bg * H * 4,
+                                     "what": "wg_gcn_gru_predict_host_f32: only the de-normalised last timestep "
+                                             "[B, 3S] returns to the host"}
+            del ph
             if tensor_path is not None:
-                model.precision = "tf32x3"
+                model.precision = "tensor"
                 try:
                     e2e_run(2)
                     dtt = e2e_run(e2e_steps)
@@ -752,7 +775,7 @@ def main():
         nominal_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
         path_tflops = FLOP_PER_SEQ * Bg * passes * steps / (ms * 1e-3) / 1e12  # per GPU
         hbm_gbs = BYTES_PER_SEQ * Bg * passes * steps / (ms * 1e-3) / 1e9      # per GPU, algorithmic
-        kname = "inproj_kernel" if flags == 0 else "inproj_tc_kernel"
+        kname = "inproj_kernel" if flags == 0 else "inproj_tc2_kernel"
         traffic, traffic_note = ncu_traffic_bytes(kname, inproj_bytes)
         stage_flops = {"gcn": 2 * (2 * S * S * F + 2 * S * F * F) * rows, "inproj": inproj_flops,
                        "recur": 2 * H * 3 * H * rows}
