@@ -171,10 +171,16 @@ def ncu_traffic_bytes(kernel_name: str, algorithmic_bytes: float):
     The kernel is matched by its full demangled base name; a capture whose traffic is not within
     [0.5, 3] x the algorithmic bytes is rejected (it would be another workload's launch).
     Returns (bytes or None, note)."""
-    try:
-        with open(NCU_SUMMARY) as f:
-            summ = json.load(f)
-    except (OSError, ValueError):
+    summ = {"kernels": []}
+    for path in (NCU_SUMMARY, NCU_SUMMARY.replace("r02_", "r02_tensor_")):   # FP32-path / tensor-path captures
+        try:
+            with open(path) as f:
+                part = json.load(f)
+            summ["kernels"] += part.get("kernels", [])
+            summ.setdefault("command", part.get("command", ""))
+        except (OSError, ValueError):
+            continue
+    if not summ["kernels"]:
         return None, "no committed capture (profiles/r02_ncu_summary.json)"
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
     for k in summ.get("kernels", []):

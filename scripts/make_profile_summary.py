@@ -8,7 +8,8 @@ os.makedirs(out_dir, exist_ok=True)
 g = os.path.join(ROOT, "gpurun_out")
 
 # ---- launch list (gpu__time_duration per launch; cold-cache, serialised: compare shares) ----
-rows = [r for r in csv.reader(open(os.path.join(g, "launches.csv"))) if len(r) > 5]
+launch_file = sys.argv[3] if len(sys.argv) > 3 else "launches.csv"
+rows = [r for r in csv.reader(open(os.path.join(g, launch_file))) if len(r) > 5]
 hdr = rows[0]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 launches = [(r[ki], float(r[vi].replace(",", "")), r[ui]) for r in rows[1:]]
@@ -16,16 +17,17 @@ with open(os.path.join(out_dir, f"{tag}_launches.csv"), "w") as f:
     f.write("kernel,gpu__time_duration.sum,unit\n")
     for k, v, u in launches:
         f.write(f"\"{k}\",{v},{u}\n")
-ours = [(k, v) for k, v, _ in launches if "wg::" in k or "pack_params" in k]
+ours = [(k, v) for k, v, _ in launches if "wg::" in k or "pack_" in k]
 step = {}
 for k, v in ours:
-    name = "gcn" if "gcn_kernel" in k else "inproj" if "inproj" in k else "recur" if "gru_recur" in k else "pack"
-    step.setdefault(name, []).append(v)
+    base = k.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0].replace("void ", "").replace("wg::", "").strip()
+    step.setdefault(base.split("<")[0], []).append(v)
 share = {k: sum(v) / len(v) for k, v in step.items()}
 tot = sum(share.values())
 
 # ---- full-set metrics of the three hot kernels ----
-raw = subprocess.run(["ncu", "-i", os.path.join(g, "prof.ncu-rep"), "--page", "raw", "--csv"],
+rep = sys.argv[2] if len(sys.argv) > 2 else "prof.ncu-rep"
+raw = subprocess.run(["ncu", "-i", os.path.join(g, rep), "--page", "raw", "--csv"],
                      capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw)))
 h = rr[0]
@@ -36,7 +38,8 @@ keep = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "smsp__inst_executed.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "launch__shared_mem_per_block_dynamic"]
+        "launch__shared_mem_per_block_dynamic", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "sm__cycles_elapsed.max"]
 kernels = []
 for r in rr[2:]:
     d = {"kernel": r[col("Kernel Name")]}
@@ -49,7 +52,8 @@ for r in rr[2:]:
                 d[k] = r[c]
             d[k + ".unit"] = rr[1][c]
     kernels.append(d)
-summary = {"tag": tag, "command": "python scripts/profile_step.py (B=4096, S=34, T=168: bench workload)",
+summary = {"tag": tag, "command": "python scripts/profile_step.py 2 (B=4096, S=34, T=168: the bench workload, fp32 path) "
+                                     "+ `... 2 4096 tensor` for the tensor-path kernels",
            "launch_share_ns": share, "launch_share_frac": {k: v / tot for k, v in share.items()}, "kernels": kernels}
 json.dump(summary, open(os.path.join(out_dir, f"{tag}_ncu_summary.json"), "w"), indent=1)
 with open(os.path.join(out_dir, f"{tag}_ncu_summary.md"), "w") as f:
@@ -58,7 +62,7 @@ with open(os.path.join(out_dir, f"{tag}_ncu_summary.md"), "w") as f:
     f.write("| kernel | ns per launch | share of step |\n|---|---:|---:|\n")
     for k, v in share.items():
         f.write(f"| {k} | {v:,.0f} | {v / tot:.1%} |\n")
-    f.write("\n`ncu --set full` of one launch each:\n\n| kernel | ms | DRAM read GB | DRAM write GB | FMA pipe active % | issue active % | regs | grid x block |\n|---|---:|---:|---:|---:|---:|---:|---|\n")
+    f.write("\n`ncu --set full` of one launch each:\n\n| kernel | ms | DRAM read GB | DRAM write GB | FMA pipe active % | tensor pipe active % | L2->SM GB | issue active % | regs | grid x block |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|---|\n")
     for d in kernels:
         def unit_gb(key):
             v, u = d.get(key, 0.0), d.get(key + ".unit", "")
@@ -67,6 +71,8 @@ with open(os.path.join(out_dir, f"{tag}_ncu_summary.md"), "w") as f:
         tu = d.get("gpu__time_duration.sum.unit", "")
         t_ms = t * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(tu, 1)
         f.write(f"| {d['kernel'][:60]} | {t_ms:.3f} | {unit_gb('dram__bytes_read.sum'):.3f} | {unit_gb('dram__bytes_write.sum'):.3f} | "
-                f"{d.get('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 0):.1f} | {d.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0):.1f} | "
+                f"{d.get('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 0):.1f} | "
+                f"{d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 0):.1f} | {unit_gb('l1tex__m_xbar2l1tex_read_bytes.sum'):.2f} | "
+                f"{d.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0):.1f} | "
                 f"{d.get('launch__registers_per_thread', 0):.0f} | {d.get('launch__grid_size', 0):.0f} x {d.get('launch__block_size', 0):.0f} |\n")
 print(open(os.path.join(out_dir, f"{tag}_ncu_summary.md")).read())
