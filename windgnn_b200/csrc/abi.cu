@@ -68,7 +68,7 @@ struct Plan {
     int I, G;      // S*Fo, 3H
     int IP;        // K of the projection GEMM: I rounded up to 16
     int NPB;       // rows of packed w_ih: G rounded up to 64
-    int GP;        // leading dim of GI: G rounded up to 4
+    int GP;        // leading dim of GI: G rounded up to 8
     int KP;        // K of the recurrent GEMM: H rounded up to 4
     int NPR;       // columns of packed w_hh^T: G rounded up to 80 (one warp's column block)
     bool sparse;   // CSR graph path: adds the Z scratch of the sparse GCN kernels
@@ -110,7 +110,7 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
         return fail(WG_ERR_UNSUPPORTED, "tensor-core projection: unsupported gate width 3H = %d", p.G);
     p.IP = p.tc ? p.tc2.KP : wg::round_up(p.I, wg::kIpBK);
     p.NPB = wg::round_up(p.G, wg::kIpBN);
-    p.GP = wg::round_up(p.G, 4);
+    p.GP = wg::round_up(p.G, 8);   // GI rows 32-byte aligned (256-bit stores in the tensor-path projection)
     p.KP = wg::round_up(H, 4);
     p.NPR = wg::recur_np(p.G);
     {

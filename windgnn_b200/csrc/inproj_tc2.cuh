@@ -8,19 +8,21 @@
 // inproj_tc_kernel (first generation, TF32 hi / lo copies of both operands in HBM) moved 11.1 GB from L2
 // for 2.06 GB of algorithmic operand bytes and was L2-bound with the tensor pipe 49 % busy (ncu r01).
 // Here the GCN kernel's ordinary fp32 tiles are the A operand: a stage's [32 k][128 rows] fp32 block
-// arrives by one bulk copy, eight converter warps split it into fp16 hi / lo in the UMMA K-major layout
+// arrives by one bulk copy, four converter warps split it into fp16 hi / lo in the UMMA K-major layout
 // in shared memory (never in HBM), and kind::f16 halves both the operand bytes and the MMA time of
 // kind::tf32.  W_ih is pre-split once per call (pack kernel) and streamed from L2 one stage at a time.
 //
 // One persistent CTA per SM, 14 warps:
 //   warp 12      producer: per stage two bulk async copies (A fp32 16 KB, B hi+lo 20 KB at N = 160)
-//   warps 4-11   converters: a thread takes 2 rows x 8 k's (8-byte loads), splits fp32 -> fp16 hi / lo and
+//   warps 8-11   converters: a thread takes 2 rows x 8 k's (8-byte loads), splits fp32 -> fp16 hi / lo and
 //                writes 16-byte chunks into the canonical layout ([k / 8][row][8 halves]: 8-row x 16-byte
 //                core matrices, SBO = 128 B, LBO = rows * 16 B)
 //   warp 13      MMA issuer: 6 x tcgen05.mma.kind::f16 (M = 128, N <= 160, K = 16) per stage;
 //                hi.hi into one TMEM accumulator, the corrections into a second one (TMEM accumulation
 //                truncates: the small terms are kept apart and added in fp32 in the epilogue)
-//   warps 0-3    epilogue: tcgen05.ld, sum, + bias, 16-byte stores of GI
+//   warps 0-7    epilogue: warp w reads TMEM lanes 32 (w % 4) .. and the column half w / 4: tcgen05.ld, sum,
+//                + bias, 32-byte stores (GI rows are 32-byte aligned); the accumulators are released to the
+//                issuer as soon as a warp's last block is in registers
 #pragma once
 
 #include <cuda_fp16.h>
@@ -33,8 +35,9 @@ namespace wg {
 
 constexpr int kT2BM = 128;
 constexpr int kT2BK = 32;                 // k's per pipeline stage (two MMA k-steps)
-constexpr int kT2ConvWarps = 8;
-constexpr int kT2Threads = (4 + kT2ConvWarps + 2) * 32;   // epilogue, converters, producer, MMA issuer
+constexpr int kT2EpiWarps = 8;            // two per TMEM lane quarter: each takes half of the tile's columns
+constexpr int kT2ConvWarps = 4;
+constexpr int kT2Threads = (kT2EpiWarps + kT2ConvWarps + 2) * 32;   // epilogue, converters, producer, MMA issuer
 constexpr int kT2MaxN = 160;              // gate columns per CTA tile (two accumulators of N columns in TMEM)
 
 struct Tc2Shape {
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);        // one arrival per epilogue warp
+        mbar_init(tmem_empty, kT2EpiWarps);   // one arrival per epilogue warp
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc_cols = (uint32_t)N_each;   // accumulators: [0, N) hi.hi, [N, 2N) corrections
 
-    if (warp == 4 + kT2ConvWarps) {
+    if (warp == kT2EpiWarps + kT2ConvWarps) {
         // ===================== producer =====================
         int s = 0;
         uint32_t phase = 0;
@@ -151,42 +154,46 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                 if (++s == stages) { s = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 4 + kT2ConvWarps) {
-        // ===================== converters: thread = (row pair, 8-k chunk) =====================
-        const int ct = tid - 128;                 // 0 .. 255
-        const int rp = ct & 63, c = ct >> 6;      // rows 2 rp, 2 rp + 1; k's 8 c .. 8 c + 7 of the stage
+    } else if (warp >= kT2EpiWarps && warp < kT2EpiWarps + kT2ConvWarps) {
+        // ===================== converters: item = (row pair, 8-k chunk), two items per thread and stage ==========
+        const int ct = tid - kT2EpiWarps * 32;    // 0 .. 127
         int s = 0;
         uint32_t phase = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(&full_ld[s], phase);
                 unsigned char* st = smem_t2 + (size_t)s * stage_bytes;
-                const float* a32 = reinterpret_cast<const float*>(st) + (c * 8) * kT2BM + 2 * rp;   // [k][128 rows]
-                unsigned char* hi = st + a32_bytes + c * (kT2BM * 16) + (2 * rp) * 16;             // [chunk][row][8 halves]
-                unsigned char* lo = hi + a16_bytes;
-                float2 v[8];
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) v[kk] = *reinterpret_cast<const float2*>(a32 + kk * kT2BM);
-                __half2 h0[4], l0[4], h1[4], l1[4];   // row 2 rp / row 2 rp + 1: k pairs
+                for (int it = 0; it < (kT2BM / 2) * (kT2BK / 8) / (kT2ConvWarps * 32); ++it) {
+                    const int item = ct + it * kT2ConvWarps * 32;
+                    const int rp = item & 63, c = item >> 6;      // rows 2 rp, 2 rp + 1; k's 8 c .. 8 c + 7 of the stage
+                    const float* a32 = reinterpret_cast<const float*>(st) + (c * 8) * kT2BM + 2 * rp;   // [k][128 rows]
+                    unsigned char* hi = st + a32_bytes + c * (kT2BM * 16) + (2 * rp) * 16;             // [chunk][row][8 halves]
+                    unsigned char* lo = hi + a16_bytes;
+                    float2 v[8];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    h0[q] = __floats2half2_rn(v[2 * q].x, v[2 * q + 1].x);
-                    h1[q] = __floats2half2_rn(v[2 * q].y, v[2 * q + 1].y);
-                    const float2 b0 = __half22float2(h0[q]), b1 = __half22float2(h1[q]);
-                    l0[q] = __floats2half2_rn(v[2 * q].x - b0.x, v[2 * q + 1].x - b0.y);
-                    l1[q] = __floats2half2_rn(v[2 * q].y - b1.x, v[2 * q + 1].y - b1.y);
+                    for (int kk = 0; kk < 8; ++kk) v[kk] = *reinterpret_cast<const float2*>(a32 + kk * kT2BM);
+                    __half2 h0[4], l0[4], h1[4], l1[4];   // row 2 rp / row 2 rp + 1: k pairs
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        h0[q] = __floats2half2_rn(v[2 * q].x, v[2 * q + 1].x);
+                        h1[q] = __floats2half2_rn(v[2 * q].y, v[2 * q + 1].y);
+                        const float2 b0 = __half22float2(h0[q]), b1 = __half22float2(h1[q]);
+                        l0[q] = __floats2half2_rn(v[2 * q].x - b0.x, v[2 * q + 1].x - b0.y);
+                        l1[q] = __floats2half2_rn(v[2 * q].y - b1.x, v[2 * q + 1].y - b1.y);
+                    }
+                    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<uint4*>(h0);
+                    *reinterpret_cast<uint4*>(hi + 16) = *reinterpret_cast<uint4*>(h1);
+                    *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<uint4*>(l0);
+                    *reinterpret_cast<uint4*>(lo + 16) = *reinterpret_cast<uint4*>(l1);
                 }
-                *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<uint4*>(h0);
-                *reinterpret_cast<uint4*>(hi + 16) = *reinterpret_cast<uint4*>(h1);
-                *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<uint4*>(l0);
-                *reinterpret_cast<uint4*>(lo + 16) = *reinterpret_cast<uint4*>(l1);
                 fence_async_smem();   // the converted operand is read by the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_cv[s]);
                 if (++s == stages) { s = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 4 + kT2ConvWarps + 1) {
+    } else if (warp == kT2EpiWarps + kT2ConvWarps + 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = umma_idesc_f16(kT2BM, N_each);
         const uint32_t lbo_a = kT2BM * 16, lbo_b = (uint32_t)N_each * 16, sbo = 128;
@@ -225,40 +232,59 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             acc_phase ^= 1;
         }
     } else {
-        // ===================== epilogue (warps 0-3 <-> TMEM lanes 32w .. 32w+31) =====================
+        // ===================== epilogue: warp w <-> TMEM lanes 32 (w % 4) .., column half w / 4 =====================
         uint32_t acc_phase = 0;
+        const int lq = warp & 3, ch = warp >> 2;
+        const int half_cols = (N_each / 2 + 15) / 16 * 16;     // columns per half, multiple of 16
+        const int cbeg = ch * half_cols, cend = (ch + 1) * half_cols < N_each ? (ch + 1) * half_cols : N_each;
+        const bool wide = (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0;   // 32-byte aligned rows
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long mt = tile / n_nt;
             const int nt = (int)(tile - mt * n_nt);
             mbar_wait(tmem_full, acc_phase);
             tc_fence_after();
-            const long long row = mt * kT2BM + warp * 32 + lane;
+            const long long row = mt * kT2BM + lq * 32 + lane;
             float* crow = C + (size_t)(row < M ? row : 0) * ldc;
-            const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-            for (int c0 = 0; c0 < N_each; c0 += 32) {
+            const uint32_t lane_base = tmem_base + ((uint32_t)(lq * 32) << 16);
+            for (int c0 = cbeg; c0 < cend; c0 += 32) {
                 float v0[32], v1[32];
-                tmem_ld32(lane_base + c0, v0);
+                tmem_ld32(lane_base + c0, v0);              // (reads past cend stay inside the allocated columns)
                 tmem_ld32(lane_base + acc_cols + c0, v1);
+                if (c0 + 32 >= cend) {   // this warp's last block is in registers: its share of the accumulators is free
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                }
                 if (row < M) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int cl = c0 + 4 * q;            // column inside the slice
+                    for (int q = 0; q < 4; ++q) {
+                        const int cl = c0 + 8 * q;            // column inside the slice
                         const int c = nt * N_each + cl;       // gate column
-                        if (cl < N_each && c < ldc) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
-                            float4 o;
-                            o.x = (v0[4 * q] + v1[4 * q]) + b4.x;
-                            o.y = (v0[4 * q + 1] + v1[4 * q + 1]) + b4.y;
-                            o.z = (v0[4 * q + 2] + v1[4 * q + 2]) + b4.z;
-                            o.w = (v0[4 * q + 3] + v1[4 * q + 3]) + b4.w;
-                            *reinterpret_cast<float4*>(crow + c) = o;
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = v0[8 * q + e] + v1[8 * q + e];
+                        if (cl + 8 <= cend && c + 8 <= ldc && wide) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(crow + c),
+                                         "f"(o[0] + b0.x), "f"(o[1] + b0.y), "f"(o[2] + b0.z), "f"(o[3] + b0.w),
+                                         "f"(o[4] + b1.x), "f"(o[5] + b1.y), "f"(o[6] + b1.z), "f"(o[7] + b1.w)
+                                         : "memory");
+                        } else {
+#pragma unroll
+                            for (int hq = 0; hq < 2; ++hq) {
+                                const int c4 = c + 4 * hq;
+                                if (cl + 4 * hq < cend && c4 < ldc) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c4));
+                                    *reinterpret_cast<float4*>(crow + c4) =
+                                        make_float4(o[4 * hq] + b4.x, o[4 * hq + 1] + b4.y, o[4 * hq + 2] + b4.z,
+                                                    o[4 * hq + 3] + b4.w);
+                                }
+                            }
                         }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
             acc_phase ^= 1;
         }
     }

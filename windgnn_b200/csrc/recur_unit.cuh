@@ -45,7 +45,7 @@ __host__ __device__ inline bool recur_u_applies(int H) { return recur_u_hp2(H) /
 __host__ __device__ inline int recur_u_hs_stride(int KP) { return ((KP / 4) & 1) ? KP : KP + 4; }
 __host__ __device__ inline size_t recur_u_smem_floats(int H, int R) {
     const int KP = round_up(H, 4), HP2 = recur_u_hp2(H), WPG = recur_u_wpg(H), NGRP = kRuWarps / WPG;
-    const int GP = round_up(3 * H, 4);
+    const int GP = round_up(3 * H, 8);
     size_t n = (size_t)KP * 3 * HP2;                          // W_hh^T as [k][gate][unit]
     n = round_up((int)n, 4);
     n += 2 * (size_t)NGRP * R * recur_u_hs_stride(KP);        // h, double buffered
@@ -72,7 +72,7 @@ struct RuFrag {
     float2 w[4][3];   // w[kk][g] = W_g[k + kk][2p .. 2p+1]
 };
 
-// GI  [B*T][ldg]   gi with b_ih (+ b_hh for r, z) folded in, column g*H + j; ldg = 3H rounded up to 4
+// GI  [B*T][ldg]   gi with b_ih (+ b_hh for r, z) folded in, column g*H + j; ldg = 3H rounded up to 8
 // Whu [KP][3][HP2] W_hh^T, Whu[k][g][j] = w_hh[g*H + j][k], zero padded
 // out [B][T][H];   gsave (SAVE): [B*T][ldsave] = [r | z | n | W_hn h + b_hn]
 // HT > 0: the hidden size is the compile-time constant HT (every shared-memory offset becomes an
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kRuThreads, 1)
     constexpr int NG = WPG * 32;           // threads per group
     extern __shared__ __align__(16) float smem[];
     const int H = HT > 0 ? HT : H_rt;
-    const int KP = round_up(H, 4), HP2 = recur_u_hp2(H), NS = HP2 >> 1, ldg = round_up(3 * H, 4);
+    const int KP = round_up(H, 4), HP2 = recur_u_hp2(H), NS = HP2 >> 1, ldg = round_up(3 * H, 8);
     const int RS = recur_u_hs_stride(KP);
     float* Ws = smem;                                                // [KP][3][HP2]
     float* hs = Ws + round_up(KP * 3 * HP2, 4);                      // [2][NGRP * R][RS]
