@@ -24,8 +24,8 @@
 // A CTA holds W_hh (hi + lo, 172 KB at H = 102) in shared memory and runs two independent groups of 16
 // sequences.  A group = 8 warps: warps 0-3 (TMEM lanes 0..127 = hidden units) take its sequences 0-7,
 // warps 4-7 its sequences 8-15.  Per step the group's warps do the gate math, write h_t, meet at a named
-// barrier, ONE thread of the group issues the 42 MMAs of the next step and commits them to the group's
-// mbarrier, on which all eight warps then wait (their next gi values are already in flight).  The two
+// barrier, three threads of the group (one per gate tile) issue the 42 MMAs of the next step and commit them
+// to the group's mbarrier, on which all eight warps then wait (their next gi values are already in flight).  The two
 // groups never synchronise with each other, so one group's product (tensor pipe) overlaps the other's
 // gate math (MUFU / ALU).  The hi.hi and hi.lo products share one N = 32 MMA (B rows = h_hi | h_lo), so
 // A_hi is read from shared memory once for both.
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kRtThreads, 1)
         for (int e = tid; e < (int)(kRtGroups * b_grp / 4); e += kRtThreads) z[e] = 0u;
     }
     if (tid == 0) {
-        for (int g = 0; g < kRtGroups; ++g) mbar_init(&acc_full[g], 1);
+        for (int g = 0; g < kRtGroups; ++g) mbar_init(&acc_full[g], 3);   // one commit per gate tile
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -259,17 +259,22 @@ __global__ void __launch_bounds__(kRtThreads, 1)
             // warp of the group has read its accumulators: one thread issues the next step's product
             fence_async_smem();
             group_barrier(1 + g, kRtGroupWarps * 32);
-            if (gt == 0) {
+            if ((gt & 31) == 0 && gt < 96) {
+                // three issuing threads per group (lane 0 of its warps 0, 1, 2), one gate tile each: the 14 MMAs of
+                // a gate are issued back to back (descriptors advance by constant increments) and committed to
+                // the group's mbarrier, which completes when all three commits have
                 tc_fence_after();
-                for (int q = 0; q < 3; ++q) {
-                    const uint32_t ah = sa + (uint32_t)q * NCH * 2048, al = ah + a_part;
-                    for (int ks = 0; ks < NKS; ++ks) {
-                        const uint64_t da_hi = umma_desc_kmajor(ah + ks * 2 * 2048, 2048, 128);
-                        const uint64_t da_lo = umma_desc_kmajor(al + ks * 2 * 2048, 2048, 128);
-                        const uint64_t db = umma_desc_kmajor(sbg + ks * 2 * kRtBLbo, kRtBLbo, 128);
-                        umma_f16(dcol + q * 2 * kRtN, da_hi, db, idesc32, ks != 0);           // hi.hi | hi.lo
-                        umma_f16(dcol + q * 2 * kRtN + kRtN, da_lo, db, idesc16, 1);          // lo.hi
-                    }
+                const int q = gt >> 5;
+                uint64_t da_hi = umma_desc_kmajor(sa + (uint32_t)q * NCH * 2048, 2048, 128);
+                uint64_t da_lo = umma_desc_kmajor(sa + a_part + (uint32_t)q * NCH * 2048, 2048, 128);
+                uint64_t db = umma_desc_kmajor(sbg, kRtBLbo, 128);
+                const uint32_t d0 = dcol + q * 2 * kRtN;
+                for (int ks = 0; ks < NKS; ++ks) {
+                    umma_f16(d0, da_hi, db, idesc32, ks != 0);            // hi.hi | hi.lo
+                    umma_f16(d0 + kRtN, da_lo, db, idesc16, 1);           // lo.hi
+                    da_hi += (2 * 2048) >> 4;                             // start-address field: 16-byte units
+                    da_lo += (2 * 2048) >> 4;
+                    db += (2 * kRtBLbo) >> 4;
                 }
                 umma_commit(&acc_full[g]);
             }
