@@ -8,11 +8,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "gcn.cuh"
 #include "gcn_bwd.cuh"
 #include "gcn_rows.cuh"
 #include "gcn_sparse.cuh"
+#include "gcn_sparse_plan.cuh"
 #include "gru_bwd.cuh"
 #include "inproj.cuh"
 #include "inproj_tc.cuh"
@@ -72,6 +74,8 @@ struct Plan {
     int KP;        // K of the recurrent GEMM: H rounded up to 4
     int NPR;       // columns of packed w_hh^T: G rounded up to 80 (one warp's column block)
     bool sparse;   // CSR graph path: adds the Z scratch of the sparse GCN kernels
+    bool sq;       // CSR graph path on gcn_sparse_plan_kernel (constant-bank weights + gather plan)
+    size_t off_sqw, off_sqplan;
     bool tc;       // tensor-core (3xTF32 tcgen05) input projection: U and w_ih kept as hi + lo
     wg::Tc2Shape tc2;
     size_t off_wp, off_bias, off_wht, off_whu, off_bhn, off_u, off_gi, off_z, total;
@@ -89,6 +93,8 @@ long long default_chunk(long long B, size_t bytes_per_seq) {
     }
     return B < c ? (B < 1 ? 1 : B) : c;
 }
+
+bool force_legacy();
 
 int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H, long long chunk,
               bool sparse = false, int flags = 0) {
@@ -139,6 +145,11 @@ int make_plan(Plan& p, long long B, int T, int S, int Fi, int Fh, int Fo, int H,
     p.off_gi = o;   o = align_up(o + rows_gi * p.GP * 4);
     // sparse path scratch: row-major U (rows x S*Fo) + one [Fo][S] row per resident CTA
     p.off_z = o;    if (sparse) o = align_up(o + (rows + wg::kNumSMs) * (size_t)S * Fo * 4);
+    // second-generation CSR kernel: weights staged for the constant bank + the gather plan
+    p.sq = sparse && Fi <= wg::kSpF && Fo <= wg::kSpF && Fh <= wg::kSqMaxFh && !force_legacy() &&
+           wg::gcn_sparse_plan_smem_bytes(S, Fi, Fo) <= (size_t)wg::kMaxSmemOptin;
+    p.off_sqw = o;    if (p.sq) o = align_up(o + sizeof(wg::SqWeights));
+    p.off_sqplan = o; if (p.sq) o = align_up(o + wg::sq_plan_bytes(S));
     p.total = o;
     return WG_OK;
 }
@@ -294,6 +305,29 @@ int launch_gcn_sparse(const Plan& p, void* ws, const Csr& g, const float* x, con
                       const float* w2, const float* b2, long long rows, cudaStream_t st) {
     if (p.Fi > wg::kSpF || p.Fo > wg::kSpF)
         return fail(WG_ERR_UNSUPPORTED, "sparse GCN: F_in / F_out must be <= %d (got %d / %d)", wg::kSpF, p.Fi, p.Fo);
+    if (p.sq && rows >= 1) {   // second generation: constant-bank weights + gather plan (prepare_sparse ran)
+        const size_t smem = wg::gcn_sparse_plan_smem_bytes(p.S, p.Fi, p.Fo);
+        const bool narrow = p.Fi <= 13 && p.Fo <= 13, exact = p.Fi == 13 && p.Fo == 13;
+        auto kern = exact ? wg::gcn_sparse_plan_kernel<13, true>
+                          : narrow ? wg::gcn_sparse_plan_kernel<13, false> : wg::gcn_sparse_plan_kernel<16, false>;
+        WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)(rows < wg::kNumSMs ? rows : wg::kNumSMs);
+        float* urow = ws_ptr<float>(ws, p.off_z);   // [rows][Fo][S] f-major U, then gridDim per-CTA Z rows
+        float* zscr = urow + (size_t)rows * p.S * p.Fo;
+        const int* steps = ws_ptr<int>(ws, p.off_sqplan);
+        const int2* plan = reinterpret_cast<const int2*>(steps + wg::round_up(wg::ceil_div(p.S, 32), 4));
+        kern<<<grid, wg::kSqThreads, smem, st>>>(x, g.rowptr, g.colidx, g.vals, steps, plan, zscr, urow, rows, p.S,
+                                                 p.Fi, p.Fh, p.Fo);
+        WG_CUDA(cudaGetLastError());
+        const long long rt = (rows + wg::kSpThreads - 1) / wg::kSpThreads * wg::kSpThreads;  // whole tiles (zero rows)
+        const dim3 tg((unsigned)((p.S + 31) / 32), (unsigned)(rt / 32));
+        if (tg.y > 65535u) return fail(WG_ERR_UNSUPPORTED, "sparse GCN: chunk of %lld rows too large", rows);
+        const size_t tsmem = wg::fmajor_to_tiles_smem_bytes(p.Fo);
+        WG_CUDA(cudaFuncSetAttribute(wg::fmajor_to_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        wg::fmajor_to_tiles_kernel<<<tg, 256, tsmem, st>>>(urow, ws_ptr<float>(ws, p.off_u), rows, p.S, p.Fo, p.IP);
+        WG_CUDA(cudaGetLastError());
+        return WG_OK;
+    }
     // a whole row's [S, F] slab fits shared memory: the row-resident fused kernel
     const size_t smem_row = wg::gcn_sparse_row_smem_bytes(p.S, p.Fi, p.Fh, p.Fo);
     if (smem_row <= (size_t)wg::kMaxSmemOptin && rows >= 1) {
@@ -540,6 +574,43 @@ int run_chunk(const Plan& p, void* ws, const float* adj, const float* x, const f
     rc = launch_inproj(p, ws, rows, st);
     if (rc) return rc;
     return launch_recur(p, ws, out, Bc, st);
+}
+
+// Per-call setup of the second-generation CSR kernel: weights into the constant bank, gather plan.
+// The constant bank is one per device: forwards on different streams are ordered through an event (a later
+// call's upload waits for the earlier call's last GCN kernel), the host side is serialised by a mutex that
+// the caller holds from prepare_sparse to finish_sparse.
+std::mutex g_sq_mu;
+struct SqDeviceState { cudaEvent_t ev = nullptr; cudaStream_t last = nullptr; bool recorded = false; };
+SqDeviceState g_sq_dev[64];
+
+int prepare_sparse(const Plan& p, void* ws, const Csr& g, const float* w1, const float* b1, const float* w2,
+                   const float* b2, int device, cudaStream_t st) {
+    wg::SqWeights* stage = ws_ptr<wg::SqWeights>(ws, p.off_sqw);
+    wg::sq_pack_weights_kernel<<<32, 256, 0, st>>>(w1, b1, w2, b2, stage, p.Fi, p.Fh, p.Fo);
+    WG_CUDA(cudaGetLastError());
+    int* steps = ws_ptr<int>(ws, p.off_sqplan);
+    int2* plan = reinterpret_cast<int2*>(steps + wg::round_up(wg::ceil_div(p.S, 32), 4));
+    const int wbs = wg::ceil_div(p.S, 32);
+    wg::csr_plan_kernel<<<wg::ceil_div(wbs, 4), 128, 0, st>>>(g.rowptr, g.colidx, g.vals, p.S, steps, plan);
+    WG_CUDA(cudaGetLastError());
+    SqDeviceState& d = g_sq_dev[device & 63];
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone && d.recorded && d.last != st) WG_CUDA(cudaStreamWaitEvent(st, d.ev, 0));
+    WG_CUDA(cudaMemcpyToSymbolAsync(wg::c_sq, stage, sizeof(wg::SqWeights), 0, cudaMemcpyDeviceToDevice, st));
+    return WG_OK;
+}
+int finish_sparse(int device, cudaStream_t st) {
+    SqDeviceState& d = g_sq_dev[device & 63];
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return WG_OK;
+    if (!d.ev) WG_CUDA(cudaEventCreateWithFlags(&d.ev, cudaEventDisableTiming));
+    WG_CUDA(cudaEventRecord(d.ev, st));
+    d.last = st;
+    d.recorded = true;
+    return WG_OK;
 }
 
 int run_chunk_csr(const Plan& p, void* ws, const Csr& g, const float* x, const float* w1, const float* b1,
@@ -849,12 +920,18 @@ int wg_gcn_gru_forward_csr_f32(const int32_t* rowptr, const int32_t* colidx, con
     if ((rc = launch_pack(p, workspace, w_ih, w_hh, b_ih, b_hh, st))) return rc;
     const Csr csr{rowptr, colidx, vals};
     const size_t x_seq = (size_t)T * S * F_in, o_seq = (size_t)T * H;
+    std::unique_lock<std::mutex> sq_lock(g_sq_mu, std::defer_lock);
+    if (p.sq) {
+        sq_lock.lock();
+        if ((rc = prepare_sparse(p, workspace, csr, w1, b1, w2, b2, device, st))) return rc;
+    }
     for (long long b0 = 0; b0 < B; b0 += p.chunk) {
         const long long Bc = (B - b0) < p.chunk ? (B - b0) : p.chunk;
         rc = run_chunk_csr(p, workspace, csr, x + (size_t)b0 * x_seq, w1, b1, w2, b2, out + (size_t)b0 * o_seq,
                            Bc, st);
         if (rc) return rc;
     }
+    if (p.sq) return finish_sparse(device, st);
     return WG_OK;
 }
 
