@@ -15,6 +15,7 @@
 #include "gcn_rows.cuh"
 #include "gcn_sparse.cuh"
 #include "gcn_sparse_plan.cuh"
+#include "gemm_kb.cuh"
 #include "gru_bwd.cuh"
 #include "inproj.cuh"
 #include "inproj_tc.cuh"
@@ -658,8 +659,8 @@ struct TrainPlan {
     size_t smem_gcn;
     int splits_hh_a, splits_hh_b, splits_ih;
     int ldu, KPd, NPd;  // dU row stride (I rounded up to 4); K / N of the dU GEMM padded for inproj_kernel
-    int mt_ih, kt_per_ih;  // dW_ih on inproj_splitk_kernel: 128-row tiles of the gate dimension, k-tiles per split
-    size_t off_acb, off_bcb;
+    int mt_ih, nt_ih;       // dW_ih on gemm_kb_kernel: tiles over the input features / the gate columns
+    long long kt_per_ih;    // k-tiles (16 rows) per split
     size_t off_gates, off_dg, off_dgt, off_wpb, off_zb, off_du, off_biasp, off_gcnp, off_splitk, total;
 };
 
@@ -727,23 +728,23 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
         const size_t rt = ((size_t)tp.rows + wg::kUTileRows - 1) / wg::kUTileRows * wg::kUTileRows;
         tp.off_dgt = o; o = align_up(o + rt * tp.KPd * 4);            // dGI in K-major 128-row tiles
         tp.off_wpb = o; o = align_up(o + (size_t)tp.NPd * tp.KPd * 4);  // w_ih packed for dU = dGI . w_ih
-        tp.off_zb = o;  o = align_up(o + (size_t)tp.NPd * 4);           // zero bias
-        tp.mt_ih = (p.G + wg::kIpBM - 1) / wg::kIpBM;
-        tp.off_acb = o; o = align_up(o + (size_t)tp.mt_ih * rt * wg::kIpBM * 4);   // dGI as column blocks [g/128][row][128]
-        tp.off_bcb = o; o = align_up(o + rt * (size_t)tp.NPd * 4);                  // U as column blocks [i/64][row][64]
-        const long long ktall = (long long)(rt / wg::kIpBK);
-        long long sp = (4LL * wg::kNumSMs) / ((long long)tp.mt_ih * (tp.NPd / wg::kIpBN));   // one wave at 4 CTAs per SM
+        tp.off_zb = o;  o = align_up(o + (size_t)tp.NPd * 4);           // zero bias (written by the pack kernel)
+        // dW_ih on gemm_kb_kernel<64, 160, 0>: tiles over (i, g), the B*T rows split so that the grid is one wave
+        tp.mt_ih = (p.IP + wg::KbWih::kBM - 1) / wg::KbWih::kBM;
+        tp.nt_ih = (p.G + wg::KbWih::kBN - 1) / wg::KbWih::kBN;
+        const long long ktall = (tp.rows + wg::kKbBK - 1) / wg::kKbBK;
+        long long sp = (3LL * wg::kNumSMs) / ((long long)tp.mt_ih * tp.nt_ih);   // one wave at 3 CTAs per SM
         if (sp < 1) sp = 1;
         if (sp > ktall) sp = ktall;
-        tp.splits_ih = (int)sp;
-        tp.kt_per_ih = (int)((ktall + sp - 1) / sp);
+        tp.kt_per_ih = (ktall + sp - 1) / sp;
+        tp.splits_ih = (int)((ktall + tp.kt_per_ih - 1) / tp.kt_per_ih);
     }
     tp.off_du = o;    o = align_up(o + (size_t)tp.rows * tp.ldu * 4);
     tp.off_biasp = o; o = align_up(o + (size_t)tp.grid_gb * 2 * tp.LD4 * 4);
     tp.off_gcnp = o;  o = align_up(o + (size_t)tp.grid_gcn * (wg::kGbwThreads / 16) * (2 * 256 + 32) * 4);
     size_t sk = (size_t)tp.splits_hh_a * 2 * H * H;
     if ((size_t)tp.splits_hh_b * H * H > sk) sk = (size_t)tp.splits_hh_b * H * H;
-    if ((size_t)tp.splits_ih * p.G * tp.ldu > sk) sk = (size_t)tp.splits_ih * p.G * tp.ldu;
+    if ((size_t)tp.splits_ih * p.I * tp.nt_ih * wg::KbWih::kBN > sk) sk = (size_t)tp.splits_ih * p.I * tp.nt_ih * wg::KbWih::kBN;
     tp.off_splitk = o; o = align_up(o + sk * 4);
     tp.total = o;
     return WG_OK;
@@ -1218,32 +1219,36 @@ int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, c
         if ((rc = splitk_gemm(a_n, hprev, H, H, rows, tp.splits_hh_b, skp, d_whh + 2 * (size_t)H * H, H, 1, st)))
             return rc;
     }
-    // 3. dW_ih [3H x I] = dGI^T . U on the projection kernel's split-K variant: both operands re-laid as
-    //    column blocks (the contraction runs over the B*T rows), one wave of CTAs, fixed-order reduction
+    // 3. dW_ih [3H x I] = dGI^T . U: gemm_kb_kernel reads dGI (row-major, as the BPTT kernel wrote it) and U (the
+    //    forward's K-major tiles) in place; one wave of CTAs over (tile, row split), fixed-order reduction
     {
-        const long long rt = (rows + wg::kUTileRows - 1) / wg::kUTileRows * wg::kUTileRows;
-        float* acb = ws_ptr<float>(workspace, tp.off_acb);
-        float* bcb = ws_ptr<float>(workspace, tp.off_bcb);
-        wg::rows_to_colblocks_kernel<<<wg::kNumSMs * 8, 256, 0, st>>>(DG, acb, rows, rt, p.G, tp.LD4, wg::kIpBM, tp.mt_ih);
+        using Cfg = wg::KbWih;
+        auto kern = wg::gemm_kb_kernel<Cfg::kBM, Cfg::kBN, Cfg::kTN>;
+        WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        wg::KbArgs a{};
+        a.a = ws_ptr<float>(workspace, p.off_u);
+        a.b = DG;
+        a.c = skp;
+        a.R = rows;
+        a.I = p.I;
+        a.IP = p.IP;
+        a.ld_dg = tp.LD4;
+        a.ldc = tp.nt_ih * Cfg::kBN;
+        a.m_tiles = tp.mt_ih;
+        a.n_tiles = tp.nt_ih;
+        a.kt_per_split = tp.kt_per_ih;
+        const dim3 grid((unsigned)(tp.mt_ih * tp.nt_ih), (unsigned)tp.splits_ih);
+        kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a);
         WG_CUDA(cudaGetLastError());
-        const dim3 tg((unsigned)(tp.NPd / 32), (unsigned)(rt / 32));
-        if (tg.y > 65535u) return fail(WG_ERR_UNSUPPORTED, "training: B*T = %lld rows exceed one pass", rows);
-        wg::tiles_to_colblocks_kernel<<<tg, 256, 0, st>>>(ws_ptr<float>(workspace, p.off_u), bcb, rows, rt, p.IP);
-        WG_CUDA(cudaGetLastError());
-        const int n_tiles = tp.NPd / wg::kIpBN;
-        WG_CUDA(cudaFuncSetAttribute(wg::inproj_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     wg::kIpSmemBytes));
-        const dim3 grid((unsigned)(tp.mt_ih * n_tiles), (unsigned)tp.splits_ih);
-        wg::inproj_splitk_kernel<<<grid, wg::kIpThreads, wg::kIpSmemBytes, st>>>(acb, bcb, skp, p.G, rt, tp.ldu, n_tiles,
-                                                                                tp.kt_per_ih);
-        WG_CUDA(cudaGetLastError());
+        // d_wih[g][i] = sum_z part[z][i][g]
         const long long total = (long long)p.G * p.I;
-        wg::sg_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(skp, tp.splits_ih, p.G, p.I, d_wih, p.I, 1,
-                                                                             tp.ldu);
+        wg::sg_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(skp, tp.splits_ih, p.I, p.G, d_wih, 1, p.I,
+                                                                             a.ldc);
         WG_CUDA(cudaGetLastError());
     }
     // 4. dU [BT x I] = dGI . W_ih on the forward's projection kernel (bulk-copy pipeline, 87 % of the FMA
-    //    peak): dGI re-laid into K-major 128-row tiles, w_ih packed as [N/64][K][64], zero bias
+    //    peak): dGI re-laid into K-major 128-row tiles, w_ih packed as [N/64][K][64], zero bias.  (A variant
+    //    of gemm_kb_kernel that reads dGI in place ran this product in 3.60 ms against 0.32 + 3.01 ms here.)
     {
         float* DGt = ws_ptr<float>(workspace, tp.off_dgt);
         float* wpb = ws_ptr<float>(workspace, tp.off_wpb);
@@ -1266,7 +1271,7 @@ int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, c
     if (tp.fp_gcn == 13) rc = launch_gcn_bwd_t<13, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
     else rc = launch_gcn_bwd_t<16, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
     if (rc) return rc;
-    wg::gcn_bwd_finish_kernel<<<(2 * 256 + 32 + 127) / 128, 128, 0, st>>>(
+    wg::gcn_bwd_finish_kernel<<<(2 * 256 + 32 + 7) / 8, 256, 0, st>>>(
         ws_ptr<float>(workspace, tp.off_gcnp), tp.grid_gcn * (wg::kGbwThreads / 16), F_in, F_hid, F_out, d_w1, d_b1,
         d_w2, d_b2);
     WG_CUDA(cudaGetLastError());

@@ -368,14 +368,19 @@ __global__ void __launch_bounds__(kGbwThreads, 1)
     }
 }
 
-// dW1 [Fi][Fh], db1 [Fh], dW2 [Fh][Fo], db2 [Fo] = sums of the partials, ascending order.
-__global__ void gcn_bwd_finish_kernel(const float* __restrict__ part, int nparts, int Fi, int Fh, int Fo,
-                                      float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
-                                      float* __restrict__ db2) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// dW1 [Fi][Fh], db1 [Fh], dW2 [Fh][Fo], db2 [Fo] = sums of the partials in a fixed order: one warp per output
+// element, lane l adds partials l, l + 32, ... ascending, then a shuffle tree (deterministic; the serial loop
+// over the 148 x 16 partials of round 1 took 0.10 ms).  grid = ceil(544 / 8) blocks of 256 threads.
+__global__ void __launch_bounds__(256) gcn_bwd_finish_kernel(const float* __restrict__ part, int nparts, int Fi, int Fh,
+                                                              int Fo, float* __restrict__ dW1, float* __restrict__ db1,
+                                                              float* __restrict__ dW2, float* __restrict__ db2) {
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (e >= 2 * 256 + 32) return;
     float s = 0.0f;
-    for (int z = 0; z < nparts; ++z) s += part[(size_t)z * (2 * 256 + 32) + e];
+    for (int z = lane; z < nparts; z += 32) s += part[(size_t)z * (2 * 256 + 32) + e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane != 0) return;
     if (e < 256) {
         const int f = e >> 4, fo = e & 15;
         if (f < Fi && fo < Fh) dW1[f * Fh + fo] = s;

@@ -126,130 +126,3 @@ __global__ void __launch_bounds__(kIpThreads, 4)
 }
 
 }  // namespace wg
-
-namespace wg {
-
-// Split-K variant for the weight gradient dW_ih = dGI^T . U of the training step (K = B*T rows): the same
-// 128 x 64 tile, bulk-copy ring and FFMA2 inner loop; blockIdx.y selects a contiguous range of k-tiles and
-// the partial sums go to Cpart[z][M][ldc] (added in a fixed order by sg_reduce_kernel).  No bias.
-__global__ void __launch_bounds__(kIpThreads, 4)
-    inproj_splitk_kernel(const float* __restrict__ At, const float* __restrict__ Bt, float* __restrict__ Cpart,
-                         long long M, long long K, int ldc, int n_tiles, int kt_per_split) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* stage0 = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kIpStages * kIpStageBytes);
-
-    const int tid = threadIdx.x;
-    const long long tile = blockIdx.x;
-    const int nt = (int)(tile % n_tiles);
-    const long long mt = tile / n_tiles;
-    const long long KTall = K / kIpBK;
-    const long long kt0 = (long long)blockIdx.y * kt_per_split;
-    const int KT = (int)((KTall - kt0) < kt_per_split ? (KTall - kt0 > 0 ? KTall - kt0 : 0) : kt_per_split);
-    const float* a_src = At + (size_t)mt * K * kIpBM + (size_t)kt0 * kIpBK * kIpBM;
-    const float* b_src = Bt + (size_t)nt * K * kIpBN + (size_t)kt0 * kIpBK * kIpBN;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kIpStages; ++s) mbar_init(&bars[s], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    auto issue = [&](int kt) {
-        const int slot = kt % kIpStages;
-        float* dst = stage0 + slot * kIpStageFloats;
-        mbar_expect_tx(&bars[slot], kIpStageBytes);
-        bulk_g2s(dst, a_src + (size_t)kt * kIpBK * kIpBM, kIpBK * kIpBM * 4, &bars[slot]);
-        bulk_g2s(dst + kIpBK * kIpBM, b_src + (size_t)kt * kIpBK * kIpBN, kIpBK * kIpBN * 4, &bars[slot]);
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kIpStages - 1; ++s)
-            if (s < KT) issue(s);
-    }
-    const int ty = tid >> 3, tx = tid & 7;
-    float2 acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
-
-    for (int kt = 0; kt < KT; ++kt) {
-        __syncthreads();
-        if (tid == 0 && kt + kIpStages - 1 < KT) issue(kt + kIpStages - 1);
-        const int slot = kt % kIpStages;
-        mbar_wait(&bars[slot], (kt / kIpStages) & 1);
-        const float* as = stage0 + slot * kIpStageFloats + ty * 4;
-        const float* bs = stage0 + slot * kIpStageFloats + kIpBK * kIpBM + tx * 4;
-#pragma unroll
-        for (int k = 0; k < kIpBK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(as + k * kIpBM);
-            const float4 a1 = *reinterpret_cast<const float4*>(as + k * kIpBM + 64);
-            const float4 b0 = *reinterpret_cast<const float4*>(bs + k * kIpBN);
-            const float4 b1 = *reinterpret_cast<const float4*>(bs + k * kIpBN + 32);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
-                                  make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float2 aa = make_float2(av[i], av[i]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(aa, bp[j], acc[i][j]);
-            }
-        }
-    }
-    float* C = Cpart + (size_t)blockIdx.y * M * ldc;
-    const int n0 = nt * kIpBN;
-    const long long m0 = mt * kIpBM;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const long long gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-        if (gm < M) {
-            float* crow = C + (size_t)gm * ldc;
-            const int c0 = n0 + tx * 4, c1 = n0 + 32 + tx * 4;
-            if (c0 < ldc) *reinterpret_cast<float4*>(crow + c0) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
-            if (c1 < ldc) *reinterpret_cast<float4*>(crow + c1) = make_float4(acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y);
-        }
-    }
-}
-
-// src [R][lds] row-major (first C columns used) -> column blocks dst[(c / CB)][Rt][CB], zero filled for
-// r >= R and c >= C: the K-major operand tiles of inproj_splitk_kernel when the contraction runs over rows.
-__global__ void rows_to_colblocks_kernel(const float* __restrict__ src, float* __restrict__ dst, long long R,
-                                         long long Rt, int C, int lds, int CB, int n_blocks) {
-    const long long total = (long long)n_blocks * Rt * CB;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int cl = (int)(e % CB);
-        const long long t = e / CB;
-        const long long r = t % Rt;
-        const int c = (int)(t / Rt) * CB + cl;
-        dst[e] = (r < R && c < C) ? __ldg(src + (size_t)r * lds + c) : 0.0f;
-    }
-}
-
-// U in the forward's K-major 128-row tiles [r / 128][IP][128] -> column blocks dst[(i / 64)][Rt][64]
-// (32 x 32 shared-memory transpose; rows >= R and columns >= IP are zero filled).
-// grid = (64 * ceil(I / 64) / 32, Rt / 32).
-__global__ void __launch_bounds__(256) tiles_to_colblocks_kernel(const float* __restrict__ Ut, float* __restrict__ dst,
-                                                                  long long R, long long Rt, int IP) {
-    __shared__ float t[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const long long r0 = (long long)blockIdx.y * 32;
-    const int i0 = blockIdx.x * 32;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int i = i0 + ty + 8 * q;
-        const long long r = r0 + tx;
-        t[ty + 8 * q][tx] = (r < R && i < IP) ? __ldg(Ut + (size_t)(r >> 7) * IP * 128 + (size_t)i * 128 + (r & 127)) : 0.0f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const long long r = r0 + ty + 8 * q;
-        const int i = i0 + tx;
-        dst[(size_t)(i >> 6) * Rt * 64 + (size_t)r * 64 + (i & 63)] = t[tx][ty + 8 * q];
-    }
-}
-
-}  // namespace wg
