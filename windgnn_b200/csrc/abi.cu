@@ -12,6 +12,7 @@
 
 #include "gcn.cuh"
 #include "gcn_bwd.cuh"
+#include "gcn_bwd_rows.cuh"
 #include "gcn_rows.cuh"
 #include "gcn_sparse.cuh"
 #include "gcn_sparse_plan.cuh"
@@ -655,7 +656,8 @@ struct TrainPlan {
     int HP, GR, bt_gb; // gru_bwd: H rounded up to 4, padded contraction length, sequences per CTA (16 or 4)
     long long rows;    // B * T
     int grid_gb;       // CTAs of the backward recurrence
-    int grid_gcn, rb_gcn, sg_gcn, fp_gcn;
+    int grid_gcn, rb_gcn, sg_gcn, fp_gcn, parts_gcn;   // parts_gcn: partial gradient sets the GCN backward writes
+    bool gcn_rows;       // gcn_bwd_rows_kernel (13 / 13 / 13 features, S <= 48), else gcn_bwd_kernel
     size_t smem_gcn;
     int splits_hh_a, splits_hh_b, splits_ih;
     int ldu, KPd, NPd;  // dU row stride (I rounded up to 4); K / N of the dU GEMM padded for inproj_kernel
@@ -701,24 +703,35 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
     // puts 7 warps instead of 4 on the SM
     tp.sg_gcn = 4;
     tp.fp_gcn = (Fi == 13 && Fh == 13 && Fo == 13) ? 13 : 16;
-    const int NSG = wg::ceil_div(S, tp.sg_gcn);
-    if (NSG > wg::kGcnThreads) return fail(WG_ERR_UNSUPPORTED, "training: S=%d too large for the dense GCN kernels", S);
-    int RB = wg::kGbwThreads / NSG;
-    const int cols = S * Fi, dcols = S * Fo;
-    (void)dcols;  // dU rows are padded to 16 bytes by construction
-    const int need = (cols % 4 == 0) ? 1 : (cols % 2 == 0) ? 2 : 4;
-    if (RB > need) RB -= RB % need;
     tp.ldu = wg::round_up(p.I, 4);
     tp.KPd = wg::round_up(p.G, wg::kIpBK);
     tp.NPd = wg::round_up(p.I, wg::kIpBN);
-    auto smem_of = [&](int rb) { return wg::gcn_bwd_smem_floats<4>(S, tp.ldu, rb) * 4; };
-    while (smem_of(RB) > (size_t)wg::kMaxSmemOptin && RB > 1) RB = (RB > need) ? RB - need : RB - 1;
-    if (smem_of(RB) > (size_t)wg::kMaxSmemOptin)
-        return fail(WG_ERR_UNSUPPORTED, "training: S=%d does not fit the shared-memory GCN backward", S);
-    tp.rb_gcn = RB;
-    tp.smem_gcn = smem_of(RB);
-    const long long nblk = (tp.rows + RB - 1) / RB;
-    tp.grid_gcn = (int)(nblk < wg::kNumSMs ? nblk : wg::kNumSMs);
+    tp.gcn_rows = wg::gcn_bwd_rows_applies(S, Fi, Fh, Fo) &&
+                  wg::gcn_bwd_rows_smem_floats(S, tp.ldu) * 4 <= (size_t)wg::kMaxSmemOptin;
+    if (tp.gcn_rows) {
+        tp.rb_gcn = wg::kGb2Rows;
+        tp.smem_gcn = wg::gcn_bwd_rows_smem_floats(S, tp.ldu) * 4;
+        const long long nblk = (tp.rows + wg::kGb2Rows - 1) / wg::kGb2Rows;
+        const int per_sm = tp.smem_gcn + 1024 <= (size_t)(228 * 1024) / 2 ? 2 : 1;   // 228 KB per SM, 1 KB reserved per CTA
+        tp.grid_gcn = (int)(nblk < (long long)per_sm * wg::kNumSMs ? nblk : (long long)per_sm * wg::kNumSMs);
+        tp.parts_gcn = tp.grid_gcn * wg::kGb2Slices;
+    } else {
+        const int NSG = wg::ceil_div(S, tp.sg_gcn);
+        if (NSG > wg::kGcnThreads) return fail(WG_ERR_UNSUPPORTED, "training: S=%d too large for the dense GCN kernels", S);
+        int RB = wg::kGbwThreads / NSG;
+        const int cols = S * Fi;
+        const int need = (cols % 4 == 0) ? 1 : (cols % 2 == 0) ? 2 : 4;
+        if (RB > need) RB -= RB % need;
+        auto smem_of = [&](int rb) { return wg::gcn_bwd_smem_floats<4>(S, tp.ldu, rb) * 4; };
+        while (smem_of(RB) > (size_t)wg::kMaxSmemOptin && RB > 1) RB = (RB > need) ? RB - need : RB - 1;
+        if (smem_of(RB) > (size_t)wg::kMaxSmemOptin)
+            return fail(WG_ERR_UNSUPPORTED, "training: S=%d does not fit the shared-memory GCN backward", S);
+        tp.rb_gcn = RB;
+        tp.smem_gcn = smem_of(RB);
+        const long long nblk = (tp.rows + RB - 1) / RB;
+        tp.grid_gcn = (int)(nblk < wg::kNumSMs ? nblk : wg::kNumSMs);
+        tp.parts_gcn = tp.grid_gcn * (wg::kGbwThreads / 16);
+    }
     tp.splits_hh_a = pick_splits(2 * H, H, tp.rows);
     tp.splits_hh_b = pick_splits(H, H, tp.rows);
     size_t o = p.total;
@@ -741,7 +754,7 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
     }
     tp.off_du = o;    o = align_up(o + (size_t)tp.rows * tp.ldu * 4);
     tp.off_biasp = o; o = align_up(o + (size_t)tp.grid_gb * 2 * tp.LD4 * 4);
-    tp.off_gcnp = o;  o = align_up(o + (size_t)tp.grid_gcn * (wg::kGbwThreads / 16) * (2 * 256 + 32) * 4);
+    tp.off_gcnp = o;  o = align_up(o + (size_t)tp.parts_gcn * (2 * 256 + 32) * 4);
     size_t sk = (size_t)tp.splits_hh_a * 2 * H * H;
     if ((size_t)tp.splits_hh_b * H * H > sk) sk = (size_t)tp.splits_hh_b * H * H;
     if ((size_t)tp.splits_ih * p.I * tp.nt_ih * wg::KbWih::kBN > sk) sk = (size_t)tp.splits_ih * p.I * tp.nt_ih * wg::KbWih::kBN;
@@ -1268,12 +1281,18 @@ int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, c
         WG_CUDA(cudaGetLastError());
     }
     // 5. GCN backward: dW1, db1, dW2, db2
-    if (tp.fp_gcn == 13) rc = launch_gcn_bwd_t<13, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
-    else rc = launch_gcn_bwd_t<16, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
-    if (rc) return rc;
+    if (tp.gcn_rows) {
+        WG_CUDA(cudaFuncSetAttribute(wg::gcn_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_gcn));
+        wg::gcn_bwd_rows_kernel<<<tp.grid_gcn, wg::kGb2Threads, tp.smem_gcn, st>>>(
+            x, dU, adj, w1, b1, w2, b2, ws_ptr<float>(workspace, tp.off_gcnp), tp.rows, p.S, tp.ldu);
+        WG_CUDA(cudaGetLastError());
+    } else {
+        if (tp.fp_gcn == 13) rc = launch_gcn_bwd_t<13, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
+        else rc = launch_gcn_bwd_t<16, 4>(tp, workspace, x, adj, w1, b1, w2, b2, st);
+        if (rc) return rc;
+    }
     wg::gcn_bwd_finish_kernel<<<(2 * 256 + 32 + 7) / 8, 256, 0, st>>>(
-        ws_ptr<float>(workspace, tp.off_gcnp), tp.grid_gcn * (wg::kGbwThreads / 16), F_in, F_hid, F_out, d_w1, d_b1,
-        d_w2, d_b2);
+        ws_ptr<float>(workspace, tp.off_gcnp), tp.parts_gcn, F_in, F_hid, F_out, d_w1, d_b1, d_w2, d_b2);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
