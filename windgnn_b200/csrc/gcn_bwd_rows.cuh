@@ -131,31 +131,39 @@ struct Gb2Tiles {
     float2 w1[8][2], w2[8][2];
 };
 
-// C[f0 + i][fo0 .. fo0+3] += sum_k A[k][f0 + i] * B[k][fo0 .. fo0+3], k = (row, station) pairs slice, slice + 16, ...
+// C[f0 + i][fo0 .. fo0+3] += sum_k A[k][f0 + i] * B[k][fo0 .. fo0+3], k = (row, station) pairs slice, slice + nslices, ...
 // A: slab (14 floats per station, row stride rsa).  B: station stride bs floats, row stride rsb; BVEC: 8-byte loads.
+// Loads run past the 13 (14) valid columns of a station into the next station / the row padding (always
+// inside the region): those products land in rows / columns 13 .. 15 of the tiles that nobody reads.
 template <bool BVEC>
 __device__ __forceinline__ void gb2_reduce(float2 (&c)[8][2], const float* __restrict__ A, int rsa,
                                            const float* __restrict__ B, int rsb, int bs, int nrows, int S, int f0, int fo0,
-                                           int slice) {
+                                           int slice, int nslices) {
+    const int K = nrows * S;
+    const int cnt = slice < K ? (K - slice + nslices - 1) / nslices : 0;
     int row = 0, s = slice;
     while (s >= S) { s -= S; ++row; }
-    while (row < nrows) {
-        const float* pa = A + (size_t)row * rsa + s * kGb2FS + f0;
-        const float* pb = B + (size_t)row * rsb + s * bs + fo0;
+    const float* pa = A + (size_t)row * rsa + s * kGb2FS + f0;
+    const float* pb = B + (size_t)row * rsb + s * bs + fo0;
+    // one step = nslices stations further; q_wrap row wraps of it are certain, one more when s runs past S
+    const int q_wrap = nslices / S, s_step = nslices - q_wrap * S;
+    const int da = nslices * kGb2FS + q_wrap * (rsa - S * kGb2FS), db = nslices * bs + q_wrap * (rsb - S * bs);
+    const int wa = rsa - S * kGb2FS, wb = rsb - S * bs;
+#pragma unroll 2
+    for (int n = 0; n < cnt; ++n) {
         float a[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            // f0 = 8: slots 14, 15 lie beyond the station (rows 14, 15 of the product are never used)
-            const float2 t = (f0 + 2 * q < kGb2FS) ? *reinterpret_cast<const float2*>(pa + 2 * q) : make_float2(0.0f, 0.0f);
+            const float2 t = *reinterpret_cast<const float2*>(pa + 2 * q);
             a[2 * q] = t.x; a[2 * q + 1] = t.y;
         }
         float2 b0, b1;
         if (BVEC) {
             b0 = *reinterpret_cast<const float2*>(pb);
-            b1 = (fo0 + 2 < kGb2FS) ? *reinterpret_cast<const float2*>(pb + 2) : make_float2(0.0f, 0.0f);
-        } else {   // 13 floats per station: columns >= 13 belong to the next station (products never used)
-            b0 = make_float2(pb[0], fo0 + 1 < kGrF ? pb[1] : 0.0f);
-            b1 = make_float2(fo0 + 2 < kGrF ? pb[2] : 0.0f, fo0 + 3 < kGrF ? pb[3] : 0.0f);
+            b1 = *reinterpret_cast<const float2*>(pb + 2);
+        } else {
+            b0 = make_float2(pb[0], pb[1]);
+            b1 = make_float2(pb[2], pb[3]);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -163,8 +171,10 @@ __device__ __forceinline__ void gb2_reduce(float2 (&c)[8][2], const float* __res
             c[i][0] = __ffma2_rn(aa, b0, c[i][0]);
             c[i][1] = __ffma2_rn(aa, b1, c[i][1]);
         }
-        s += kGb2Slices;
-        while (s >= S) { s -= S; ++row; }
+        s += s_step;
+        pa += da;
+        pb += db;
+        if (s >= S) { s -= S; pa += wa; pb += wb; }
     }
 }
 
@@ -177,7 +187,7 @@ __device__ __forceinline__ void gb2_block(float* __restrict__ ra, float* __restr
                                           const float* __restrict__ w1d, const float* __restrict__ b1s,
                                           const float* __restrict__ w2d, const float* __restrict__ b2s,
                                           const float* __restrict__ w2t, int S, int ldu, int s0, int s_end, int r,
-                                          int nrows, Gb2Tiles& tl, int f0, int fo0, int slice, uint64_t* bar_d,
+                                          int nrows, Gb2Tiles& tl, int f0, int fo0, int slice, int nslices, uint64_t* bar_d,
                                           unsigned phase_d, bool du_bulk, const float* __restrict__ next_x,
                                           unsigned next_x_bytes, uint64_t* bar_x) {
     const int in_cols = S * kGrF, RS = gcn_bwd_rows_rs(S);
@@ -260,7 +270,7 @@ __device__ __forceinline__ void gb2_block(float* __restrict__ ra, float* __restr
     __syncthreads();   // AG and dZ2 complete
 
     // ---- P3: dW2 += AG^T dZ2 (row 13: db2) ; then dAG = dZ2 . W2^T -> rb ----
-    gb2_reduce<false>(tl.w2, rb, RS, rc, ldu, kGrF, nrows, S, f0, fo0, slice);
+    if (slice >= 0) gb2_reduce<false>(tl.w2, rb, RS, rc, ldu, kGrF, nrows, S, f0, fo0, slice, nslices);
     {   // own dZ2 as operand pairs (reads only)
         const float* dz = rc + (size_t)r * ldu;
 #pragma unroll
@@ -317,7 +327,7 @@ __device__ __forceinline__ void gb2_block(float* __restrict__ ra, float* __restr
     }
 
     // ---- P5: dW1 += AX^T dZ1 (row 13: db1) ----
-    gb2_reduce<true>(tl.w1, ra, RS, rc, RS, kGb2FS, nrows, S, f0, fo0, slice);
+    if (slice >= 0) gb2_reduce<true>(tl.w1, ra, RS, rc, RS, kGb2FS, nrows, S, f0, fo0, slice, nslices);
     __syncthreads();   // rc and ra are free for the next block
 }
 
@@ -381,8 +391,15 @@ __global__ void __launch_bounds__(kGb2Threads, 2)
     }
     __syncthreads();
 
-    // reduction coordinates: 8 (f) x 4 (fo) output tile, slice of the (row, station) index
-    const int f0 = (tid & 1) * 8, fo0 = ((tid >> 1) & 3) * 4, slice = tid >> 3;
+    // reduction coordinates: 8 (f) x 4 (fo) output tile, slice of the (row, station) index.  The warps whose units
+    // own one more station pair than the others (S = 34: one warp with 3 + 2 pairs against 2 + 2) leave the
+    // reductions to the lighter warps — that evens out the FMA work between the CTA's barriers.
+    const int heavy_warps = (extra + 1) / 2;
+    const bool all_reduce = heavy_warps == 0 || heavy_warps == kGb2Warps;
+    const int nslices = (all_reduce ? kGb2Warps : kGb2Warps - heavy_warps) * 4;
+    const int f0 = (lane & 1) * 8, fo0 = ((lane >> 1) & 3) * 4;
+    const int slice = all_reduce ? w * 4 + (lane >> 3) : (w >= heavy_warps ? (w - heavy_warps) * 4 + (lane >> 3) : -1);
+    const int part_slot = tid >> 3;   // where this thread's partial sums go (0 .. 15)
     Gb2Tiles tl;
 #pragma unroll
     for (int i = 0; i < 8; ++i) tl.w1[i][0] = tl.w1[i][1] = tl.w2[i][0] = tl.w2[i][1] = make_float2(0.0f, 0.0f);
@@ -436,13 +453,13 @@ __global__ void __launch_bounds__(kGb2Threads, 2)
 #define WG_GB2(N)                                                                                                   \
     case N:                                                                                                         \
         gb2_block<N>(ra, rb, rc, arT, arN, astride, w1d, b1s, w2d, b2s, w2t, S, ldu, s0, s_end, r, nrows, tl, f0,   \
-                     fo0, slice, bar_d, phase_d, d_bulk, nsrc, nbytes, bar_x);                                      \
+                     fo0, slice, nslices, bar_d, phase_d, d_bulk, nsrc, nbytes, bar_x);                             \
         break;
         switch (npw) {   // warp-uniform
             WG_GB2(1) WG_GB2(2) WG_GB2(3)
             default:   // a warp without stations (S < 16) still takes part in the barriers and the reductions
                 gb2_block<1>(ra, rb, rc, arT, arN, astride, w1d, b1s, w2d, b2s, w2t, S, ldu, s0, s_end, r, nrows, tl, f0,
-                             fo0, slice, bar_d, phase_d, d_bulk, nsrc, nbytes, bar_x);
+                             fo0, slice, nslices, bar_d, phase_d, d_bulk, nsrc, nbytes, bar_x);
                 break;
         }
 #undef WG_GB2
@@ -450,7 +467,7 @@ __global__ void __launch_bounds__(kGb2Threads, 2)
     }
 
     // ---- per-thread partials: part[cta * 16 + slice][...]; row 13 of each product is the bias gradient ----
-    float* pp = part + ((size_t)blockIdx.x * kGb2Slices + slice) * kGb2PartFloats;
+    float* pp = part + ((size_t)blockIdx.x * kGb2Slices + part_slot) * kGb2PartFloats;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int f = f0 + i;
