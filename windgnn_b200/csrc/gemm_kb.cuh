@@ -17,6 +17,8 @@
 // tiles cover 442 x 306 with 5.7 % padding; 8 x 10 register tile; 128 threads = one warp per
 // scheduler (a 160-thread variant with 8 x 8 tiles ran at 51 % of the FMA pipe: the fifth warp
 // doubles one scheduler's work and the per-tile barrier makes everyone wait for it; this one 70 %).
+// (Tried: writing dGI transposed into the dU GEMM's K-major tiles from here as the tiles pass through shared
+// memory — +0.28 ms on this kernel against the 0.32 ms of the separate rows_to_tiles pass: dropped.)
 #pragma once
 
 #include "wg_common.cuh"
