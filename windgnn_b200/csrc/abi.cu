@@ -437,13 +437,16 @@ int launch_recur_ws(const Plan& p, void* ws, float* out, long long Bc, cudaStrea
 // few sequences (the reference's batch-1 calls, small shards): 4 per CTA, bit-identical results
 bool recur_small_applies(const Plan& p, long long Bc) {
     // up to two waves of 4-sequence CTAs (~0.55 ms each at T = 168) beat one pass of the 32-sequence kernel (1.4 ms)
-    return Bc <= 2LL * wg::kRsBT * wg::kNumSMs && (p.NPR / 4) * (wg::kRsBT / 2) <= wg::kRsThreads &&
+    return Bc <= 2LL * wg::kRsBT * wg::kNumSMs && p.NPR / 2 <= wg::kRsCols &&
            wg::recur_small_smem_floats(p.KP, p.NPR, p.GP) * 4 <= (size_t)wg::kMaxSmemOptin;
 }
 template <bool SAVE>
 int launch_recur_small(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
     const size_t smem = wg::recur_small_smem_floats(p.KP, p.NPR, p.GP) * 4;
-    auto kern = wg::gru_recur_small_kernel<SAVE>;
+    // FMA chains per thread = sequences per CTA that can exist (the reference's batch-1 calls run one)
+    auto kern = Bc >= 4 ? wg::gru_recur_small_kernel<SAVE, 4>
+              : Bc == 3 ? wg::gru_recur_small_kernel<SAVE, 3>
+              : Bc == 2 ? wg::gru_recur_small_kernel<SAVE, 2> : wg::gru_recur_small_kernel<SAVE, 1>;
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (Bc + wg::kRsBT - 1) / wg::kRsBT;
     if (grid < 1) return WG_OK;

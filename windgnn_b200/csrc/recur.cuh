@@ -403,7 +403,8 @@ namespace wg {
 // (chunking / sharding invariance is tested bit-exactly).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRsBT = 4;        // sequences per CTA
-constexpr int kRsThreads = 192;
+constexpr int kRsCols = 192;     // gate-column pairs a CTA can hold (3H <= 384)
+constexpr int kRsThreads = 2 * kRsCols;   // 12 warps: the product runs on the first NP / 2 threads, the gate math on all
 
 __host__ __device__ inline size_t recur_small_smem_floats(int KP, int NP, int GP) {
     size_t n = (size_t)KP * NP;            // W_hh^T
@@ -414,7 +415,70 @@ __host__ __device__ inline size_t recur_small_smem_floats(int KP, int NP, int GP
     return n;
 }
 
-template <bool SAVE>
+// One step's product for one gate-column pair and the NS sequences of the CTA that exist:
+// gh[i][2cp .. 2cp+1] = sum_k h[i][k] * W_hh^T[k][2cp .. 2cp+1], k ascending in ONE FFMA2 chain per sequence.
+// Stages of KS k's (8 for one or two chains, 4 for three or four), double buffered in registers: a stage's FMAs
+// (>= 36 cycles) cover the shared-memory latency of the next stage's operands even with a single chain.
+// N4: number of 4-k groups actually used of the stage (the last stage of a KS = 8 loop may be half full).
+template <int NS, int KS, int N4>
+__device__ __forceinline__ void rs_load(const float* __restrict__ wp, const float* __restrict__ hs, int k, int NP, int RS,
+                                        float4 (&hh)[NS][KS / 4], float2 (&ww)[KS]) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int q = 0; q < N4; ++q) hh[i][q] = *reinterpret_cast<const float4*>(hs + i * RS + k + 4 * q);
+#pragma unroll
+    for (int kk = 0; kk < 4 * N4; ++kk) ww[kk] = *reinterpret_cast<const float2*>(wp + (size_t)(k + kk) * NP);
+}
+template <int NS, int KS, int N4>
+__device__ __forceinline__ void rs_fma(float2 (&acc)[NS], const float4 (&hh)[NS][KS / 4], const float2 (&ww)[KS]) {
+#pragma unroll
+    for (int kk = 0; kk < 4 * N4; ++kk) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const float4 q = hh[i][kk >> 2];
+            const float a = (kk & 3) == 0 ? q.x : (kk & 3) == 1 ? q.y : (kk & 3) == 2 ? q.z : q.w;
+            acc[i] = __ffma2_rn(make_float2(a, a), ww[kk], acc[i]);
+        }
+    }
+}
+template <int NS>
+__device__ __forceinline__ void rs_gemm(const float* __restrict__ wp, const float* __restrict__ hs, float* __restrict__ gh,
+                                        int KP, int NP, int RS) {
+    constexpr int KS = NS <= 2 ? 8 : 4, G4 = KS / 4;
+    float2 acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) acc[i] = make_float2(0.0f, 0.0f);
+    float4 hA[NS][G4], hB[NS][G4];
+    float2 wA[KS], wB[KS];
+    // KP is a multiple of 4: `full` stages of KS, then (KS = 8 only) possibly one half stage (`tail`)
+    const int full = KP / KS;
+    const bool tail = (KP % KS) != 0;
+    if (full > 0) rs_load<NS, KS, G4>(wp, hs, 0, NP, RS, hA, wA);
+    else if (tail) rs_load<NS, KS, 1>(wp, hs, 0, NP, RS, hA, wA);
+    int s8 = 0;
+#pragma unroll 1
+    for (; s8 + 2 <= full; s8 += 2) {
+        rs_load<NS, KS, G4>(wp, hs, (s8 + 1) * KS, NP, RS, hB, wB);
+        rs_fma<NS, KS, G4>(acc, hA, wA);
+        if (s8 + 2 < full) rs_load<NS, KS, G4>(wp, hs, (s8 + 2) * KS, NP, RS, hA, wA);
+        else if (tail) rs_load<NS, KS, 1>(wp, hs, (s8 + 2) * KS, NP, RS, hA, wA);
+        rs_fma<NS, KS, G4>(acc, hB, wB);
+    }
+    if (s8 < full) {   // one full stage left in A
+        if (tail) rs_load<NS, KS, 1>(wp, hs, (s8 + 1) * KS, NP, RS, hB, wB);
+        rs_fma<NS, KS, G4>(acc, hA, wA);
+        if (tail) rs_fma<NS, KS, 1>(acc, hB, wB);
+    } else if (tail) {
+        rs_fma<NS, KS, 1>(acc, hA, wA);
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) *reinterpret_cast<float2*>(gh + i * NP) = acc[i];
+}
+
+// NB: FMA chains per thread = min(4, batch) (a kernel parameter rather than a per-CTA switch: with the four
+// variants inlined behind one switch ptxas hoists across the cases and spills).
+template <bool SAVE, int NB>
 __global__ void __launch_bounds__(kRsThreads, 1)
     gru_recur_small_kernel(const float* __restrict__ GI, const float* __restrict__ WhT, const float* __restrict__ bhn,
                            float* __restrict__ out, long long B, int T, int H, int ldg, int KP, int NP,
@@ -441,55 +505,49 @@ __global__ void __launch_bounds__(kRsThreads, 1)
     for (int e = tid; e < kRsBT * NP; e += kRsThreads) ghs[e] = 0.0f;
     for (int e = tid; e < KP; e += kRsThreads) bns[e] = e < H ? __ldg(bhn + e) : 0.0f;
 
-    // gi rows of step t -> buffer (t & 1): 16-byte chunks (ldg is a multiple of 4, rows 16-byte aligned)
+    // gi rows of step t -> buffer (t & 1): 16-byte chunks (ldg is a multiple of 4, rows 16-byte aligned).  The
+    // copies are issued by the UPPER half of the CTA (the lower half runs the product and should start on it at
+    // once); each of those threads owns fixed chunks whose source advances by one row per step — no index
+    // arithmetic inside the time loop.
     const int chunks = ldg >> 2;
-    auto prefetch = [&](int t) {
-        float* dstb = gis + (t & 1) * kRsBT * ldg;
-        for (int e = tid; e < kRsBT * chunks; e += kRsThreads) {
-            const int b = e / chunks, c = e - b * chunks;
-            const bool ok = b0 + b < B;
-            const float* src = GI + ((size_t)(ok ? b0 + b : 0) * T + t) * ldg + 4 * c;
-            cp_async16(dstb + b * ldg + 4 * c, src, ok);
-        }
-        cp_async_commit();
-    };
+    constexpr int kPfThreads = kRsThreads - kRsCols, kPfMax = (kRsBT * (4 * 128) / 4 + kPfThreads - 1) / kPfThreads;
+    const float* pf_src[kPfMax];
+    int pf_off[kPfMax];       // float offset inside a gi buffer, -1: no chunk
+    bool pf_ok[kPfMax];
+#pragma unroll
+    for (int q = 0; q < kPfMax; ++q) {
+        const int e = (tid - kRsCols) + q * kPfThreads;
+        const bool mine = tid >= kRsCols && e < kRsBT * chunks;
+        const int b = mine ? e / chunks : 0, c = mine ? e - b * chunks : 0;
+        pf_ok[q] = mine && (b0 + b < B);
+        pf_off[q] = mine ? b * ldg + 4 * c : -1;
+        pf_src[q] = GI + ((size_t)(pf_ok[q] ? b0 + b : 0) * T) * ldg + 4 * c;
+    }
+    // every thread commits a group (empty for the lower half): the waits below count groups
+#define WG_RS_PREFETCH(t_)                                                                              \
+    do {                                                                                                \
+        float* dstb_ = gis + ((t_) & 1) * kRsBT * ldg;                                                  \
+        _Pragma("unroll") for (int q = 0; q < kPfMax; ++q)                                              \
+            if (pf_off[q] >= 0) cp_async16(dstb_ + pf_off[q], pf_src[q] + (size_t)(t_) * ldg, pf_ok[q]); \
+        cp_async_commit();                                                                              \
+    } while (0)
     __syncthreads();
-    prefetch(0);
+    WG_RS_PREFETCH(0);
 
-    // GEMM coordinates: every thread of the first NP / 2 owns one gate-column pair for all 4 sequences
+    // GEMM coordinates: the first NP / 2 threads own one gate-column pair each, for the NB = min(4, batch)
+    // sequences a CTA can have: NB FMA chains per thread (round 1 always ran 4 — for the reference's batch-1 calls three
+    // quarters of the FMAs went to sequences that do not exist).  The k loop (rs_gemm) is software-pipelined by
+    // hand (ncu: the loop waited on LDS).
+    // Every output's sum is still ONE chain over k ascending: bit-identical to every other recurrence kernel.
     const int cp = tid;
+    const int nb = (int)((B - b0) < kRsBT ? (B - b0) : kRsBT);   // sequences of this CTA that exist
     const bool gemm_thread = cp < (NP >> 1);
 
     for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) prefetch(t + 1);
+        if (t + 1 < T) WG_RS_PREFETCH(t + 1);
         const float* g = gis + (t & 1) * kRsBT * ldg;
-        if (gemm_thread) {
-            float2 acc[kRsBT];
-#pragma unroll
-            for (int i = 0; i < kRsBT; ++i) acc[i] = make_float2(0.0f, 0.0f);
-            if (t > 0) {   // h_{-1} = 0: the product is zero at t == 0
-                const float* wp = Ws + 2 * cp;
-#pragma unroll 2
-                for (int k = 0; k < KP; k += 4) {
-                    float4 h[kRsBT];
-                    float2 w[4];
-#pragma unroll
-                    for (int i = 0; i < kRsBT; ++i) h[i] = *reinterpret_cast<const float4*>(hs + i * RS + k);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float2*>(wp + (size_t)(k + kk) * NP);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-                        for (int i = 0; i < kRsBT; ++i) {
-                            const float a = kk == 0 ? h[i].x : kk == 1 ? h[i].y : kk == 2 ? h[i].z : h[i].w;
-                            acc[i] = __ffma2_rn(make_float2(a, a), w[kk], acc[i]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kRsBT; ++i) *reinterpret_cast<float2*>(ghs + i * NP + 2 * cp) = acc[i];
-        }
+        if (t > 0 && gemm_thread)   // h_{-1} = 0: the product is zero at t == 0 (ghs was zeroed above)
+            rs_gemm<NB>(Ws + 2 * cp, hs, ghs + 2 * cp, KP, NP, RS);
         // gi(t) was committed one step ago (or before the loop); only step t+1's group may still be in flight
         if (t + 1 < T) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();   // gi(t) and gh(t) complete
@@ -499,7 +557,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
 #pragma unroll
         for (int u = 0; u < (kRsBT * 128 + kRsThreads - 1) / kRsThreads; ++u) {
             const int e = tid + u * kRsThreads;
-            if (e < kRsBT * H) {
+            if (e < nb * H) {
                 const int b = e / H, j = e - b * H;
                 const float* gr = g + b * ldg + j;
                 const float* gh = ghs + b * NP + j;
@@ -523,6 +581,7 @@ __global__ void __launch_bounds__(kRsThreads, 1)
         }
         __syncthreads();   // h(t) visible before the next GEMM; gi buffer (t & 1) and gh free again
     }
+#undef WG_RS_PREFETCH
 }
 
 }  // namespace wg
