@@ -440,16 +440,40 @@ bool recur_small_applies(const Plan& p, long long Bc) {
     return Bc <= 2LL * wg::kRsBT * wg::kNumSMs && p.NPR / 2 <= wg::kRsCols &&
            wg::recur_small_smem_floats(p.KP, p.NPR, p.GP) * 4 <= (size_t)wg::kMaxSmemOptin;
 }
+template <bool SAVE, int NB, int KPT>
+int launch_recur_regw_t(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
+    const size_t smem = wg::recur_regw_smem_floats(KPT, p.NPR, p.GP) * 4;
+    auto kern = wg::gru_recur_regw_kernel<SAVE, NB, KPT>;
+    WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (Bc + wg::kRsBT - 1) / wg::kRsBT;
+    kern<<<(unsigned)grid, wg::kRwThreads, smem, st>>>(ws_ptr<float>(ws, p.off_gi), ws_ptr<float>(ws, p.off_wht),
+                                                      ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, p.GP, p.NPR,
+                                                      gsave, ldsave);
+    WG_CUDA(cudaGetLastError());
+    return WG_OK;
+}
+template <bool SAVE, int KPT>
+int launch_recur_regw(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
+    // FMA chains per thread = sequences per CTA that can exist (the reference's batch-1 calls run one)
+    if (Bc >= 4) return launch_recur_regw_t<SAVE, 4, KPT>(p, ws, out, Bc, st, gsave, ldsave);
+    if (Bc == 3) return launch_recur_regw_t<SAVE, 3, KPT>(p, ws, out, Bc, st, gsave, ldsave);
+    if (Bc == 2) return launch_recur_regw_t<SAVE, 2, KPT>(p, ws, out, Bc, st, gsave, ldsave);
+    return launch_recur_regw_t<SAVE, 1, KPT>(p, ws, out, Bc, st, gsave, ldsave);
+}
+
 template <bool SAVE>
 int launch_recur_small(const Plan& p, void* ws, float* out, long long Bc, cudaStream_t st, float* gsave, int ldsave) {
+    if (Bc < 1) return WG_OK;
+    // W_hh in registers for the contraction lengths of the shipped models (H = 102 -> 104, H = 21 -> 24)
+    if (p.NPR <= wg::kRwThreads && p.KP == 104) return launch_recur_regw<SAVE, 104>(p, ws, out, Bc, st, gsave, ldsave);
+    if (p.NPR <= wg::kRwThreads && p.KP == 24) return launch_recur_regw<SAVE, 24>(p, ws, out, Bc, st, gsave, ldsave);
     const size_t smem = wg::recur_small_smem_floats(p.KP, p.NPR, p.GP) * 4;
-    // FMA chains per thread = sequences per CTA that can exist (the reference's batch-1 calls run one)
+    // FMA chains per thread = sequences per CTA that can exist
     auto kern = Bc >= 4 ? wg::gru_recur_small_kernel<SAVE, 4>
               : Bc == 3 ? wg::gru_recur_small_kernel<SAVE, 3>
               : Bc == 2 ? wg::gru_recur_small_kernel<SAVE, 2> : wg::gru_recur_small_kernel<SAVE, 1>;
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (Bc + wg::kRsBT - 1) / wg::kRsBT;
-    if (grid < 1) return WG_OK;
     kern<<<(unsigned)grid, wg::kRsThreads, smem, st>>>(ws_ptr<float>(ws, p.off_gi), ws_ptr<float>(ws, p.off_wht),
                                                       ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, p.GP, p.KP,
                                                       p.NPR, gsave, ldsave);

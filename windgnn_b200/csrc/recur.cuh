@@ -584,4 +584,127 @@ __global__ void __launch_bounds__(kRsThreads, 1)
 #undef WG_RS_PREFETCH
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small-batch recurrence with W_hh IN REGISTERS (compile-time contraction length KPT).
+//
+// gru_recur_small_kernel streams W_hh^T (127 KB at H = 102) out of shared memory every timestep: ~1000
+// cycles of LSU time per step even when the CTA holds ONE sequence, which is the reference's own
+// call pattern (`model(adj_matrix, batch_x)` with batch 1, src/main.py:66,102).  Here a thread owns one
+// gate COLUMN and keeps its KPT weights in registers for the whole kernel; a step's product is KPT
+// FFMAs per sequence in one dependent chain (k ascending: bit-identical to every other recurrence
+// kernel), fed by broadcast 16-byte loads of h.  Shared memory holds only h, gi and gh (17 KB).
+// Gate math, gi prefetch and outputs as in gru_recur_small_kernel.  Serves 3H (padded) <= 320.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRwThreads = 320;   // 10 warps >= the 306 gate columns of H = 102
+
+__host__ __device__ inline size_t recur_regw_smem_floats(int KP, int NP, int GP) {
+    return (size_t)kRsBT * (KP + 4) + 2 * (size_t)kRsBT * GP + (size_t)kRsBT * NP + (size_t)KP;
+}
+
+template <bool SAVE, int NB, int KPT>
+__global__ void __launch_bounds__(kRwThreads, 1)
+    gru_recur_regw_kernel(const float* __restrict__ GI, const float* __restrict__ WhT, const float* __restrict__ bhn,
+                          float* __restrict__ out, long long B, int T, int H, int ldg, int NP, float* __restrict__ gsave,
+                          int ldsave) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int RS = KPT + 4;
+    float* hs = smem;                          // [4][RS]
+    float* gis = hs + kRsBT * RS;              // [2][4][ldg]
+    float* ghs = gis + 2 * kRsBT * ldg;        // [4][NP]
+    float* bns = ghs + kRsBT * NP;             // [KPT]
+    const int tid = threadIdx.x;
+    const long long b0 = (long long)blockIdx.x * kRsBT;
+    const int H2 = 2 * H;
+
+    // this thread's gate column of W_hh^T ([KPT][NP], zero padded): registers for the whole kernel
+    const bool gemm_thread = tid < NP;
+    float w[KPT];
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) w[k] = gemm_thread ? __ldg(WhT + (size_t)k * NP + tid) : 0.0f;
+
+    for (int e = tid; e < kRsBT * RS; e += kRwThreads) hs[e] = 0.0f;
+    for (int e = tid; e < 2 * kRsBT * ldg; e += kRwThreads) gis[e] = 0.0f;
+    for (int e = tid; e < kRsBT * NP; e += kRwThreads) ghs[e] = 0.0f;
+    for (int e = tid; e < KPT; e += kRwThreads) bns[e] = e < H ? __ldg(bhn + e) : 0.0f;
+
+    // gi rows of step t -> buffer (t & 1): each thread owns fixed 16-byte chunks whose source advances one row per step
+    const int chunks = ldg >> 2;
+    constexpr int kPfMax = (kRsBT * (4 * 128) / 4 + kRwThreads - 1) / kRwThreads;
+    const float* pf_src[kPfMax];
+    int pf_off[kPfMax];       // float offset inside a gi buffer, -1: no chunk
+    bool pf_ok[kPfMax];
+#pragma unroll
+    for (int q = 0; q < kPfMax; ++q) {
+        const int e = tid + q * kRwThreads;
+        const bool mine = e < kRsBT * chunks;
+        const int b = mine ? e / chunks : 0, c = mine ? e - b * chunks : 0;
+        pf_ok[q] = mine && (b0 + b < B);
+        pf_off[q] = mine ? b * ldg + 4 * c : -1;
+        pf_src[q] = GI + ((size_t)(pf_ok[q] ? b0 + b : 0) * T) * ldg + 4 * c;
+    }
+#define WG_RW_PREFETCH(t_)                                                                              \
+    do {                                                                                                \
+        float* dstb_ = gis + ((t_) & 1) * kRsBT * ldg;                                                  \
+        _Pragma("unroll") for (int q = 0; q < kPfMax; ++q)                                              \
+            if (pf_off[q] >= 0) cp_async16(dstb_ + pf_off[q], pf_src[q] + (size_t)(t_) * ldg, pf_ok[q]); \
+        cp_async_commit();                                                                              \
+    } while (0)
+    __syncthreads();
+    WG_RW_PREFETCH(0);
+
+    const int nb = (int)((B - b0) < kRsBT ? (B - b0) : kRsBT);   // sequences of this CTA that exist
+
+    for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) WG_RW_PREFETCH(t + 1);
+        const float* g = gis + (t & 1) * kRsBT * ldg;
+        if (t > 0 && gemm_thread) {   // h_{-1} = 0: the product is zero at t == 0 (ghs was zeroed above)
+            float acc[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) acc[i] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < KPT; k += 4) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const float4 h = *reinterpret_cast<const float4*>(hs + i * RS + k);
+                    acc[i] = fmaf(h.x, w[k], acc[i]);
+                    acc[i] = fmaf(h.y, w[k + 1], acc[i]);
+                    acc[i] = fmaf(h.z, w[k + 2], acc[i]);
+                    acc[i] = fmaf(h.w, w[k + 3], acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) ghs[i * NP + tid] = acc[i];
+        }
+        if (t + 1 < T) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();   // gi(t) and gh(t) complete
+#pragma unroll
+        for (int u = 0; u < (kRsBT * 128 + kRwThreads - 1) / kRwThreads; ++u) {
+            const int e = tid + u * kRwThreads;
+            if (e < nb * H) {
+                const int b = e / H, j = e - b * H;
+                const float* gr = g + b * ldg + j;
+                const float* gh = ghs + b * NP + j;
+                const float r = sigmoid_f(gr[0] + gh[0]);
+                const float z = sigmoid_f(gr[H] + gh[H]);
+                const float hn = gh[H2] + bns[j];
+                const float n = tanh_f(gr[H2] + r * hn);
+                const float hnew = (hs[b * RS + j] - n) * z + n;
+                hs[b * RS + j] = hnew;
+                if (b0 + b < B) {
+                    out[((size_t)(b0 + b) * T + t) * H + j] = hnew;
+                    if (SAVE) {
+                        float* gs = gsave + ((size_t)(b0 + b) * T + t) * ldsave + j;
+                        gs[0] = r;
+                        gs[H] = z;
+                        gs[H2] = n;
+                        gs[H2 + H] = hn;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // h(t) visible before the next product; gi buffer (t & 1) and gh free again
+    }
+#undef WG_RW_PREFETCH
+}
+
 }  // namespace wg
