@@ -680,7 +680,8 @@ __global__ void pack_wih_bwd_kernel(const float* __restrict__ w_ih, float* __res
 struct TrainPlan {
     Plan f;            // the forward's plan (chunk == B, FP32 path, dense graph)
     int LD4;           // row stride of the gate / DG buffers: 4H rounded up to 4
-    int HP, GR, bt_gb; // gru_bwd: H rounded up to 4, padded contraction length, sequences per CTA (16 or 4)
+    int HP, GR, bt_gb; // gru_bwd: H rounded up to 4, padded contraction length, sequences per CTA
+    bool gb_regw;      // gru_bwd_regw_kernel (W_hh in registers; HP = 104 or 24), else gru_bwd_kernel
     long long rows;    // B * T
     int grid_gb;       // CTAs of the backward recurrence
     int grid_gcn, rb_gcn, sg_gcn, fp_gcn, parts_gcn;   // parts_gcn: partial gradient sets the GCN backward writes
@@ -714,13 +715,23 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
         return fail(WG_ERR_UNSUPPORTED, "training: GCN feature widths must be <= 16 (got %d / %d / %d)", Fi, Fh, Fo);
     tp.LD4 = wg::round_up(4 * H, 4);
     tp.HP = wg::round_up(H, 4);
-    // 16 sequences per CTA when that fills the machine, else 4 (the recurrence is latency-bound: with few
-    // sequences per GPU — configs[4]: 512 — more, lighter CTAs shorten every one of the T serial steps)
-    tp.bt_gb = (B > 0 ? B : 1) > 4LL * wg::kNumSMs ? wg::kGbBT : 4;
-    tp.GR = wg::gru_bwd_gr(H, tp.bt_gb);
-    if (tp.HP > 128 || (tp.HP / 4) * (tp.bt_gb / 4) * wg::gru_bwd_ksplit(tp.bt_gb) > wg::kGbThreads ||
-        wg::gru_bwd_smem_floats(tp.HP, tp.GR, tp.bt_gb) * 4 > (size_t)wg::kMaxSmemOptin)
-        return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d too large for the shared-memory BPTT kernel", H);
+    tp.gb_regw = tp.HP == 104 || tp.HP == 24;
+    if (tp.gb_regw) {
+        // W_hh in registers: the smallest CTA size that still makes the grid one wave (28 sequences fit)
+        const long long Bn = B > 0 ? B : 1;
+        tp.bt_gb = 28;
+        for (int bt : {4, 8, 16, 28})
+            if ((Bn + bt - 1) / bt <= wg::kNumSMs) { tp.bt_gb = bt; break; }
+        tp.GR = wg::gru_bwd_gr(H, 4);
+    } else {
+        // 16 sequences per CTA when that fills the machine, else 4 (the recurrence is latency-bound: with few
+        // sequences per GPU — configs[4]: 512 — more, lighter CTAs shorten every one of the T serial steps)
+        tp.bt_gb = (B > 0 ? B : 1) > 4LL * wg::kNumSMs ? wg::kGbBT : 4;
+        tp.GR = wg::gru_bwd_gr(H, tp.bt_gb);
+        if (tp.HP > 128 || (tp.HP / 4) * (tp.bt_gb / 4) * wg::gru_bwd_ksplit(tp.bt_gb) > wg::kGbThreads ||
+            wg::gru_bwd_smem_floats(tp.HP, tp.GR, tp.bt_gb) * 4 > (size_t)wg::kMaxSmemOptin)
+            return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d too large for the shared-memory BPTT kernel", H);
+    }
     if (wg::recur_smem_floats(p.KP, p.NPR, p.GP, true) * 4 > (size_t)wg::kMaxSmemOptin)
         return fail(WG_ERR_UNSUPPORTED, "training: GRU hidden size %d does not fit the shared-memory recurrence", H);
     tp.rows = (B > 0 ? B : 1) * (long long)T;
@@ -1241,10 +1252,24 @@ int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, c
 
     // 1. BPTT through the recurrence: DG = [da_r | da_z | da_n | da_n r], bias partials
     {
-        const size_t smem = wg::gru_bwd_smem_floats(tp.HP, tp.GR, tp.bt_gb) * 4;
-        auto kern = tp.bt_gb == 4 ? wg::gru_bwd_kernel<4> : wg::gru_bwd_kernel<wg::kGbBT>;
-        WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<tp.grid_gb, wg::kGbThreads, smem, st>>>(gates, out, d_out, w_hh, DG, biasp, B, T, H, tp.LD4, tp.HP, tp.GR);
+        if (tp.gb_regw) {
+            using KernT = void (*)(const float*, const float*, const float*, const float*, float*, float*, long long, int, int, int);
+            KernT kern = nullptr;
+            if (tp.HP == 104)
+                kern = tp.bt_gb == 4 ? wg::gru_bwd_regw_kernel<4, 104> : tp.bt_gb == 8 ? wg::gru_bwd_regw_kernel<8, 104>
+                     : tp.bt_gb == 16 ? wg::gru_bwd_regw_kernel<16, 104> : wg::gru_bwd_regw_kernel<28, 104>;
+            else
+                kern = tp.bt_gb == 4 ? wg::gru_bwd_regw_kernel<4, 24> : tp.bt_gb == 8 ? wg::gru_bwd_regw_kernel<8, 24>
+                     : tp.bt_gb == 16 ? wg::gru_bwd_regw_kernel<16, 24> : wg::gru_bwd_regw_kernel<28, 24>;
+            const size_t smem = wg::gru_bwd_regw_smem_floats(tp.HP, tp.bt_gb) * 4;
+            WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<tp.grid_gb, wg::kGrwThreads, smem, st>>>(gates, out, d_out, w_hh, DG, biasp, B, T, H, tp.LD4);
+        } else {
+            const size_t smem = wg::gru_bwd_smem_floats(tp.HP, tp.GR, tp.bt_gb) * 4;
+            auto kern = tp.bt_gb == 4 ? wg::gru_bwd_kernel<4> : wg::gru_bwd_kernel<wg::kGbBT>;
+            WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<tp.grid_gb, wg::kGbThreads, smem, st>>>(gates, out, d_out, w_hh, DG, biasp, B, T, H, tp.LD4, tp.HP, tp.GR);
+        }
         WG_CUDA(cudaGetLastError());
         wg::gru_bias_grad_kernel<<<(4 * H + 127) / 128, 128, 0, st>>>(biasp, tp.grid_gb * 2, H, tp.LD4, d_bih, d_bhh);
         WG_CUDA(cudaGetLastError());

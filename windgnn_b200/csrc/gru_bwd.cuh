@@ -218,6 +218,174 @@ __global__ void __launch_bounds__(kGbThreads, 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BPTT with W_hh IN REGISTERS (compile-time padded hidden size HPT).
+//
+// gru_bwd_kernel keeps W_hh (125 KB at H = 102) in shared memory: one CTA per SM, 16 sequences per
+// CTA (256 CTAs = 1.7 waves at 4096 sequences), 8.2 us per timestep — 36 % of the FMA pipe (ncu).
+// Here thread (gate g, hidden unit j) keeps its column W_hh[g*H + k][j], k < H, in registers for the
+// whole kernel and computes the partial product over ITS gate's k for every sequence of the CTA:
+//     P[g][b][j] = sum_k dgh[b][g*H + k] * W_hh[g*H + k][j]        (FFMA2 on sequence pairs)
+// dgh lives in shared memory as [gate][k][sequence] so that one broadcast 16-byte load feeds two FFMA2;
+// the three gate partials meet in the next step's gate phase (fixed order: deterministic).  Without
+// the weights shared memory holds 28 sequences (151 KB): 4096 sequences are ONE wave of 147 CTAs.
+// Gate phase, staging (cp.async during the product), DG / bias-partial outputs as in gru_bwd_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGrwThreads = 320;   // 3 gates x 104 hidden units = 312 product threads
+// dgh row stride (floats): a multiple of 4 with an odd number of 16-byte groups, so that the gate phase's
+// 16-byte stores (lanes = consecutive hidden units) are conflict free
+__host__ __device__ constexpr int gru_bwd_regw_btp(int BT) { return ((BT / 4) % 2 == 1) ? BT : BT + 4; }
+__host__ __device__ inline size_t gru_bwd_regw_smem_floats(int HPT, int BT) {
+    return 3 * (size_t)HPT * gru_bwd_regw_btp(BT)      // dgh [3][HPT][BTP]
+           + (size_t)BT * HPT                          // D = g z
+           + 3 * (size_t)BT * HPT                      // P: the three gate partials of dgh . W_hh
+           + 6 * (size_t)BT * HPT;                     // staged inputs of one step
+}
+
+template <int BT, int HPT>
+__global__ void __launch_bounds__(kGrwThreads, 1)
+    gru_bwd_regw_kernel(const float* __restrict__ gates, const float* __restrict__ out, const float* __restrict__ dout,
+                        const float* __restrict__ w_hh, float* __restrict__ DG, float* __restrict__ bias_part,
+                        long long B, int T, int H, int LD4) {
+    static_assert(BT % 4 == 0 && HPT % 4 == 0 && 3 * HPT <= kGrwThreads && HPT <= 128, "geometry");
+    extern __shared__ __align__(16) float smem[];
+    constexpr int HP = HPT, BTP = gru_bwd_regw_btp(BT), NG4 = BT / 4;
+    float* dgh = smem;                        // [3][HPT][BTP]
+    float* Dd = dgh + 3 * HPT * BTP;          // [BT][HP]
+    float* Pp = Dd + BT * HP;                 // [3][BT][HP]
+    float* stg = Pp + 3 * BT * HP;            // [6][BT][HP]
+
+    const int tid = threadIdx.x;
+    const long long b0 = (long long)blockIdx.x * BT;
+
+    // product coordinates and this thread's weights
+    const int pg = tid / HPT, pj = tid - pg * HPT;
+    const bool prod_thread = tid < 3 * HPT;
+    float w[HPT];
+#pragma unroll
+    for (int k = 0; k < HPT; ++k)
+        w[k] = (prod_thread && k < H && pj < H) ? __ldg(w_hh + ((size_t)pg * H + k) * H + pj) : 0.0f;
+
+    for (int e = tid; e < 3 * HPT * BTP; e += kGrwThreads) dgh[e] = 0.0f;
+    for (int e = tid; e < 4 * BT * HP; e += kGrwThreads) Dd[e] = 0.0f;      // D and the partials
+    for (int e = tid; e < 6 * BT * HP; e += kGrwThreads) stg[e] = 0.0f;
+
+    // ---- staging of one step's inputs: six H-long rows per sequence (as in gru_bwd_kernel) ----
+    const bool even = (H & 1) == 0 && (LD4 & 1) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(gates) | reinterpret_cast<uintptr_t>(out) |
+                        reinterpret_cast<uintptr_t>(dout)) & 7) == 0;
+    auto prefetch = [&](int t) {
+        const int per_row = even ? (H >> 1) : H;       // copies per row
+        for (int rb = tid >> 5; rb < 6 * BT; rb += kGrwThreads / 32) {
+            const int b = rb % BT, q = rb / BT;
+            const bool ok = (b0 + b < B) && !(q == 5 && t == 0);
+            const size_t row = (size_t)(b0 + b) * T + t;
+            const float* src = dout;                         // any valid address when !ok (zero fill)
+            if (ok) {
+                if (q == 0) src = dout + row * H;
+                else if (q == 5) src = out + (row - 1) * H;  // h_prev = out[b, t - 1]
+                else src = gates + row * LD4 + (size_t)(q - 1) * H;
+            }
+            float* dst = stg + ((size_t)q * BT + b) * HP;
+            if (even) {
+                for (int c = tid & 31; c < per_row; c += 32) cp_async8z(dst + 2 * c, ok ? src + 2 * c : src, ok);
+            } else {
+                for (int c = tid & 31; c < per_row; c += 32) cp_async4(dst + c, ok ? src + c : src, ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    __syncthreads();
+    prefetch(T - 1);
+
+    // gate-phase coordinates: hidden unit gj x every second group of 4 sequences (threads 256 .. 319 idle here)
+    const int gj = tid & 127;
+    const int gq = tid >> 7;               // 0 / 1: sequence groups gq, gq + 2, ...; 2: none
+    float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+
+    for (int t = T - 1; t >= 0; --t) {
+        cp_async_wait<0>();
+        __syncthreads();   // staged inputs of step t and the previous product's partials are visible
+
+        // ================= gate phase =================
+        if (gq < 2 && gj < H) {
+#pragma unroll
+            for (int grp = 0; grp < (NG4 + 1) / 2; ++grp) {
+                const int g4 = gq + 2 * grp;
+                if (g4 < NG4) {
+                    float dr[4], dz_[4], dnr[4];
+#pragma unroll
+                    for (int bl = 0; bl < 4; ++bl) {
+                        const int b = g4 * 4 + bl;
+                        const int o = b * HP + gj;
+                        const float g = ((stg[o] + Dd[o]) + Pp[o]) + (Pp[BT * HP + o] + Pp[2 * BT * HP + o]);
+                        const float r = stg[1 * BT * HP + o], z = stg[2 * BT * HP + o];
+                        const float n = stg[3 * BT * HP + o], hn = stg[4 * BT * HP + o];
+                        const float hp = stg[5 * BT * HP + o];
+                        const float dn = g * (1.0f - z);
+                        const float dz = g * (hp - n);
+                        const float da_n = dn * (1.0f - n * n);
+                        const float da_z = dz * z * (1.0f - z);
+                        const float da_r = da_n * hn * r * (1.0f - r);
+                        const float da_nr = da_n * r;
+                        Dd[o] = g * z;
+                        dr[bl] = da_r; dz_[bl] = da_z; dnr[bl] = da_nr;
+                        if (b0 + b < B) {
+                            float* dg = DG + ((size_t)(b0 + b) * T + t) * LD4;
+                            dg[gj] = da_r;
+                            dg[H + gj] = da_z;
+                            dg[2 * H + gj] = da_n;
+                            dg[3 * H + gj] = da_nr;
+                        }
+                        bsum[0] += da_r; bsum[1] += da_z; bsum[2] += da_n; bsum[3] += da_nr;
+                    }
+                    float* d = dgh + gj * BTP + g4 * 4;
+                    *reinterpret_cast<float4*>(d) = make_float4(dr[0], dr[1], dr[2], dr[3]);
+                    *reinterpret_cast<float4*>(d + HPT * BTP) = make_float4(dz_[0], dz_[1], dz_[2], dz_[3]);
+                    *reinterpret_cast<float4*>(d + 2 * HPT * BTP) = make_float4(dnr[0], dnr[1], dnr[2], dnr[3]);
+                }
+            }
+        }
+        __syncthreads();   // dgh complete; the staged inputs are free
+        if (t == 0) break;
+        prefetch(t - 1);   // lands during the product
+
+        // ================= P[g] = dgh[g] . W_hh[g] (this thread: gate pg, hidden unit pj, all sequences) =================
+        if (prod_thread) {
+            float2 acc[BT / 2];
+#pragma unroll
+            for (int i = 0; i < BT / 2; ++i) acc[i] = make_float2(0.0f, 0.0f);
+            const float* dp = dgh + pg * HPT * BTP;
+#pragma unroll
+            for (int k = 0; k < HPT; ++k) {
+                const float2 ww = make_float2(w[k], w[k]);
+#pragma unroll
+                for (int q = 0; q < NG4; ++q) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(dp + k * BTP + 4 * q);
+                    acc[2 * q] = __ffma2_rn(ww, make_float2(d4.x, d4.y), acc[2 * q]);
+                    acc[2 * q + 1] = __ffma2_rn(ww, make_float2(d4.z, d4.w), acc[2 * q + 1]);
+                }
+            }
+            float* P = Pp + pg * BT * HP + pj;
+#pragma unroll
+            for (int i = 0; i < BT / 2; ++i) {
+                P[(2 * i) * HP] = acc[i].x;
+                P[(2 * i + 1) * HP] = acc[i].y;
+            }
+        }
+    }
+
+    // ---- per-CTA column sums of DG: bias_part[(cta * 2 + gq)][LD4] ----
+    if (gq < 2 && gj < H) {
+        float* bp = bias_part + ((size_t)blockIdx.x * 2 + gq) * LD4;
+        bp[gj] = bsum[0];
+        bp[H + gj] = bsum[1];
+        bp[2 * H + gj] = bsum[2];
+        bp[3 * H + gj] = bsum[3];
+    }
+}
+
 // db_ih = [sum da_r | sum da_z | sum da_n], db_hh = [sum da_r | sum da_z | sum da_n r], summed over
 // the per-CTA partials in a fixed order.
 __global__ void gru_bias_grad_kernel(const float* __restrict__ part, int nparts, int H, int LD4,
