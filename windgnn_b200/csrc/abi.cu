@@ -500,6 +500,15 @@ int recur_u_pick_r(long long Bc, int ngrp) {
     }
     return best;
 }
+// FMA-pipe hand-over between the two groups of a scheduler (recur_unit.cuh).  Measured (scripts/handover_ab.py,
+// profiles/r02_handover_ab.json): H = 21 (one warp per group, gate-dominated steps) 0.395 -> 0.358 ms at 4096
+// sequences; H = 102 (two warps per group) within +-5 % either way — so it is on for one-warp groups only.
+// WG_RU_HANDOVER=0 / 1 overrides (results are identical either way).
+bool recur_handover(int wpg) {
+    const char* e = getenv("WG_RU_HANDOVER");
+    if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+    return wpg == 1;
+}
 bool recur_unit_applies(const Plan& p) {
     return !force_legacy() && wg::recur_u_applies(p.H) &&
            wg::recur_u_smem_floats(p.H, wg::kRuMinR) * 4 <= (size_t)wg::kMaxSmemOptin;
@@ -513,7 +522,8 @@ int launch_recur_unit_t(const Plan& p, void* ws, float* out, long long Bc, cudaS
     const long long grid = (Bc + per_cta - 1) / per_cta;
     if (grid < 1) return WG_OK;
     kern<<<(unsigned)grid, wg::kRuThreads, smem, st>>>(ws_ptr<float>(ws, p.off_gi), ws_ptr<float>(ws, p.off_whu),
-                                                      ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, gsave, ldsave);
+                                                      ws_ptr<float>(ws, p.off_bhn), out, Bc, p.T, p.H, gsave, ldsave,
+                                                      recur_handover(WPG) ? 1 : 0);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
