@@ -24,5 +24,6 @@ names = ["gemm", "cpwait+gi", "gates", "barrier"]
 for w in range(8):
     d = np.diff(a[w, 20:160, :], axis=1)
     step = a[w, 21:161, 0] - a[w, 20:160, 0]
-    print(f"B={B} warp {w}: step {step.mean():.0f} cyc | " + " ".join(f"{n_}={v:.0f}" for n_, v in zip(names, d.mean(axis=0))))
+    wait = a[w, 21:161, 0] - a[w, 20:160, 4]   # hand-over wait (+ loop overhead) before the product
+    print(f"B={B} warp {w}: step {step.mean():.0f} cyc | wait {wait.mean():.0f} | " + " ".join(f"{n_}={v:.0f}" for n_, v in zip(names, d.mean(axis=0))))
 print("gemm start offsets vs warp 0:", [(a[w, 20:160, 0] - a[0, 20:160, 0]).mean().round() for w in range(8)])

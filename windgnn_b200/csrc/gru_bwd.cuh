@@ -223,23 +223,35 @@ __global__ void __launch_bounds__(kGbThreads, 1)
 //
 // gru_bwd_kernel keeps W_hh (125 KB at H = 102) in shared memory: one CTA per SM, 16 sequences per
 // CTA (256 CTAs = 1.7 waves at 4096 sequences), 8.2 us per timestep — 36 % of the FMA pipe (ncu).
-// Here thread (gate g, hidden unit j) keeps its column W_hh[g*H + k][j], k < H, in registers for the
-// whole kernel and computes the partial product over ITS gate's k for every sequence of the CTA:
-//     P[g][b][j] = sum_k dgh[b][g*H + k] * W_hh[g*H + k][j]        (FFMA2 on sequence pairs)
-// dgh lives in shared memory as [gate][k][sequence] so that one broadcast 16-byte load feeds two FFMA2;
-// the three gate partials meet in the next step's gate phase (fixed order: deterministic).  Without
-// the weights shared memory holds 28 sequences (151 KB): 4096 sequences are ONE wave of 147 CTAs.
-// Gate phase, staging (cp.async during the product), DG / bias-partial outputs as in gru_bwd_kernel.
+// Here thread (gate g, k-half kh, hidden-unit PAIR p) keeps W_hh[g*H + k][2p, 2p+1] for its HPT/2
+// contraction indices k in registers for the whole kernel (104 registers at H = 102) and computes, for
+// every sequence of the CTA, the partial product over ITS gate and k-half:
+//     P[g][kh][b][2p, 2p+1] = sum_{k in half kh} dgh[b][g*H + k] * W_hh[g*H + k][2p, 2p+1]
+// as FFMA2 with the unit pair as the vector operand and dgh[b][k] as the broadcast scalar.  dgh lives in
+// shared memory as [gate][k][sequence], so one broadcast 16-byte load (four sequences at one k) feeds FOUR
+// FFMA2.  (First version: thread = one column, FFMA2 over sequence pairs — two FFMA2 per 16-byte load, and a
+// broadcast LDS.128 still costs two shared-memory wavefronts: ncu showed 19 K wavefronts and 30 K cycles per
+// timestep, 41 % of the warp samples waiting on shared-memory data.)  The six partials of a unit meet in the
+// next step's gate phase, added in a fixed order (deterministic).  Without the weights shared memory holds
+// 28 sequences: 4096 sequences are ONE wave of 147 CTAs.  Sequences are processed in passes of 16 so that
+// the accumulators stay at 32 registers.  Gate phase, staging (cp.async during the product), DG / bias-
+// partial outputs as in gru_bwd_kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGrwThreads = 320;   // 3 gates x 104 hidden units = 312 product threads
+constexpr int kGrwThreads = 320;   // 3 gates x 2 k-halves x 52 unit pairs = 312 product threads
 // dgh row stride (floats): a multiple of 4 with an odd number of 16-byte groups, so that the gate phase's
 // 16-byte stores (lanes = consecutive hidden units) are conflict free
 __host__ __device__ constexpr int gru_bwd_regw_btp(int BT) { return ((BT / 4) % 2 == 1) ? BT : BT + 4; }
+// staging slots (floats): a row is fetched by ONE bulk copy from the 16-byte-aligned address at or below its start,
+// so element j of the row sits at slot[m + j], m = the row's misalignment in floats (0 .. 3)
+__host__ __device__ constexpr int gru_bwd_regw_sg(int HPT) { return 4 * HPT + 4; }   // 4H floats + m, rounded up to 4
+__host__ __device__ constexpr int gru_bwd_regw_sr(int HPT) { return HPT + 4; }       // H floats + m, rounded up to 4
 __host__ __device__ inline size_t gru_bwd_regw_smem_floats(int HPT, int BT) {
     return 3 * (size_t)HPT * gru_bwd_regw_btp(BT)      // dgh [3][HPT][BTP]
            + (size_t)BT * HPT                          // D = g z
-           + 3 * (size_t)BT * HPT                      // P: the three gate partials of dgh . W_hh
-           + 6 * (size_t)BT * HPT;                     // staged inputs of one step
+           + 6 * (size_t)BT * HPT                      // P: the six (gate, k-half) partials of dgh . W_hh
+           + (size_t)BT * gru_bwd_regw_sg(HPT)         // staged gate rows [r|z|n|hn] of one step
+           + 2 * (size_t)BT * gru_bwd_regw_sr(HPT)     // staged dout and h_prev rows
+           + 4;                                        // mbarrier
 }
 
 template <int BT, int HPT>
@@ -250,53 +262,88 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
     static_assert(BT % 4 == 0 && HPT % 4 == 0 && 3 * HPT <= kGrwThreads && HPT <= 128, "geometry");
     extern __shared__ __align__(16) float smem[];
     constexpr int HP = HPT, BTP = gru_bwd_regw_btp(BT), NG4 = BT / 4;
+    constexpr int NP = HPT / 2;               // unit pairs
+    constexpr int KH = HPT / 2;               // contraction indices per k-half
     float* dgh = smem;                        // [3][HPT][BTP]
     float* Dd = dgh + 3 * HPT * BTP;          // [BT][HP]
-    float* Pp = Dd + BT * HP;                 // [3][BT][HP]
-    float* stg = Pp + 3 * BT * HP;            // [6][BT][HP]
+    float* Pp = Dd + BT * HP;                 // [6][BT][HP]   slot = gate * 2 + k-half
+    constexpr int SG = gru_bwd_regw_sg(HPT), SR = gru_bwd_regw_sr(HPT);
+    float* stG = Pp + 6 * BT * HP;            // [BT][SG]  gate rows
+    float* stD = stG + BT * SG;               // [BT][SR]  dout rows
+    float* stH = stD + BT * SR;               // [BT][SR]  h_prev rows
+    uint64_t* sbar = reinterpret_cast<uint64_t*>(stH + BT * SR);
 
     const int tid = threadIdx.x;
     const long long b0 = (long long)blockIdx.x * BT;
 
     // product coordinates and this thread's weights
-    const int pg = tid / HPT, pj = tid - pg * HPT;
-    const bool prod_thread = tid < 3 * HPT;
-    float w[HPT];
+    const int pslot = tid / NP, pp = tid - pslot * NP;
+    const int pg = pslot >> 1, pkh = pslot & 1;
+    const bool prod_thread = tid < 6 * NP;
+    float2 w2[KH];
 #pragma unroll
-    for (int k = 0; k < HPT; ++k)
-        w[k] = (prod_thread && k < H && pj < H) ? __ldg(w_hh + ((size_t)pg * H + k) * H + pj) : 0.0f;
+    for (int kk = 0; kk < KH; ++kk) {
+        const int k = pkh * KH + kk, j = 2 * pp;
+        const float* wr = w_hh + ((size_t)pg * H + k) * H + j;
+        w2[kk].x = (prod_thread && k < H && j < H) ? __ldg(wr) : 0.0f;
+        w2[kk].y = (prod_thread && k < H && j + 1 < H) ? __ldg(wr + 1) : 0.0f;
+    }
 
     for (int e = tid; e < 3 * HPT * BTP; e += kGrwThreads) dgh[e] = 0.0f;
-    for (int e = tid; e < 4 * BT * HP; e += kGrwThreads) Dd[e] = 0.0f;      // D and the partials
-    for (int e = tid; e < 6 * BT * HP; e += kGrwThreads) stg[e] = 0.0f;
+    for (int e = tid; e < 7 * BT * HP; e += kGrwThreads) Dd[e] = 0.0f;      // D and the partials
+    for (int e = tid; e < BT * (SG + 2 * SR); e += kGrwThreads) stG[e] = 0.0f;
+    if (tid == 0) {
+        mbar_init(sbar, 3 * BT);
+        fence_mbar_init();
+    }
 
-    // ---- staging of one step's inputs: six H-long rows per sequence (as in gru_bwd_kernel) ----
-    const bool even = (H & 1) == 0 && (LD4 & 1) == 0 &&
-                      ((reinterpret_cast<uintptr_t>(gates) | reinterpret_cast<uintptr_t>(out) |
-                        reinterpret_cast<uintptr_t>(dout)) & 7) == 0;
+    // ---- staging of one step's inputs: per sequence one gate row (4H floats), one dout row, one h_prev row ----
+    // Thread i < 3 BT fetches row (kind = i / BT, sequence i % BT) with ONE bulk copy and arrives on the mbarrier
+    // (count 3 BT) with the copy's byte count.  (First version: 8-byte cp.async per thread — as many instructions
+    // per step as the whole product.)  A row the aligned copy would take outside its tensor (the tensor's first /
+    // last row at most), and h_prev at t = 0, are written by the thread itself.
+    const int skind = tid / BT, sb = tid - skind * BT;
+    const size_t n_rows = (size_t)B * T;
+    auto stage_row = [&](float* slot, const float* base, size_t total, size_t g0, int n) {
+        const int m = (int)((reinterpret_cast<uintptr_t>(base + g0) >> 2) & 3);
+        const int L = (m + n + 3) & ~3;
+        if (g0 >= (size_t)m && g0 - m + L <= total) {
+            mbar_expect_tx(sbar, (unsigned)(L * 4));
+            bulk_g2s(slot, base + g0 - m, (unsigned)(L * 4), sbar);
+        } else {
+            for (int j = 0; j < n; ++j) slot[m + j] = base[g0 + j];
+            fence_proxy_async_smem();
+            mbar_arrive(sbar);
+        }
+    };
     auto prefetch = [&](int t) {
-        const int per_row = even ? (H >> 1) : H;       // copies per row
-        for (int rb = tid >> 5; rb < 6 * BT; rb += kGrwThreads / 32) {
-            const int b = rb % BT, q = rb / BT;
-            const bool ok = (b0 + b < B) && !(q == 5 && t == 0);
-            const size_t row = (size_t)(b0 + b) * T + t;
-            const float* src = dout;                         // any valid address when !ok (zero fill)
-            if (ok) {
-                if (q == 0) src = dout + row * H;
-                else if (q == 5) src = out + (row - 1) * H;  // h_prev = out[b, t - 1]
-                else src = gates + row * LD4 + (size_t)(q - 1) * H;
-            }
-            float* dst = stg + ((size_t)q * BT + b) * HP;
-            if (even) {
-                for (int c = tid & 31; c < per_row; c += 32) cp_async8z(dst + 2 * c, ok ? src + 2 * c : src, ok);
+        if (tid < 3 * BT) {
+            if (b0 + sb >= B) {
+                mbar_arrive(sbar);   // no such sequence: its slots stay zero
             } else {
-                for (int c = tid & 31; c < per_row; c += 32) cp_async4(dst + c, ok ? src + c : src, ok);
+                const size_t row = (size_t)(b0 + sb) * T + t;
+                if (skind == 0) {
+                    stage_row(stG + sb * SG, gates, n_rows * LD4, row * LD4, 4 * H);
+                } else if (skind == 1) {
+                    stage_row(stD + sb * SR, dout, n_rows * H, row * H, H);
+                } else if (t > 0) {
+                    stage_row(stH + sb * SR, out, n_rows * H, (row - 1) * H, H);   // h_prev = out[b, t - 1]
+                } else {
+                    for (int j = 0; j < SR; ++j) stH[sb * SR + j] = 0.0f;          // h_{-1} = 0
+                    fence_proxy_async_smem();
+                    mbar_arrive(sbar);
+                }
             }
         }
-        cp_async_commit();
     };
+    // misalignment (floats) of row `row` of a tensor with row stride `stride` floats whose base misalignment is a0
+    auto misal = [](int a0, long long row, int stride) { return (a0 + (int)(row & 3) * (stride & 3)) & 3; };
+    const int aG = (int)((reinterpret_cast<uintptr_t>(gates) >> 2) & 3);
+    const int aD = (int)((reinterpret_cast<uintptr_t>(dout) >> 2) & 3);
+    const int aH = (int)((reinterpret_cast<uintptr_t>(out) >> 2) & 3);
 
     __syncthreads();
+    fence_proxy_async_smem();   // the zero fills above are ordered before the first bulk copies
     prefetch(T - 1);
 
     // gate-phase coordinates: hidden unit gj x every second group of 4 sequences (threads 256 .. 319 idle here)
@@ -305,8 +352,8 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
     float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 
     for (int t = T - 1; t >= 0; --t) {
-        cp_async_wait<0>();
-        __syncthreads();   // staged inputs of step t and the previous product's partials are visible
+        mbar_wait(sbar, (unsigned)((T - 1 - t) & 1));   // staged inputs of step t have landed
+        __syncthreads();   // the previous product's partials (and thread-written slots) are visible
 
         // ================= gate phase =================
         if (gq < 2 && gj < H) {
@@ -319,10 +366,14 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
                     for (int bl = 0; bl < 4; ++bl) {
                         const int b = g4 * 4 + bl;
                         const int o = b * HP + gj;
-                        const float g = ((stg[o] + Dd[o]) + Pp[o]) + (Pp[BT * HP + o] + Pp[2 * BT * HP + o]);
-                        const float r = stg[1 * BT * HP + o], z = stg[2 * BT * HP + o];
-                        const float n = stg[3 * BT * HP + o], hn = stg[4 * BT * HP + o];
-                        const float hp = stg[5 * BT * HP + o];
+                        const long long row = (b0 + b) * T + t;
+                        const float* sg = stG + b * SG + misal(aG, row, LD4) + gj;
+                        const float g = ((stD[b * SR + misal(aD, row, H) + gj] + Dd[o]) + (Pp[o] + Pp[BT * HP + o])) +
+                                        ((Pp[2 * BT * HP + o] + Pp[3 * BT * HP + o]) +
+                                         (Pp[4 * BT * HP + o] + Pp[5 * BT * HP + o]));
+                        const float r = sg[0], z = sg[H];
+                        const float n = sg[2 * H], hn = sg[3 * H];
+                        const float hp = stH[b * SR + (t > 0 ? misal(aH, row - 1, H) : 0) + gj];
                         const float dn = g * (1.0f - z);
                         const float dz = g * (hp - n);
                         const float da_n = dn * (1.0f - n * n);
@@ -351,27 +402,36 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
         if (t == 0) break;
         prefetch(t - 1);   // lands during the product
 
-        // ================= P[g] = dgh[g] . W_hh[g] (this thread: gate pg, hidden unit pj, all sequences) =================
+        // ===== P[g][kh] = dgh[g][k-half] . W_hh[g][k-half] (this thread: gate pg, half pkh, unit pair pp, all sequences) =====
         if (prod_thread) {
-            float2 acc[BT / 2];
+            const float* dp = dgh + (pg * HPT + pkh * KH) * BTP;
+            float* P = Pp + (size_t)pslot * BT * HP + 2 * pp;
 #pragma unroll
-            for (int i = 0; i < BT / 2; ++i) acc[i] = make_float2(0.0f, 0.0f);
-            const float* dp = dgh + pg * HPT * BTP;
+            for (int q0 = 0; q0 < NG4; q0 += 4) {   // passes of up to 16 sequences
+                float2 acc[16];
 #pragma unroll
-            for (int k = 0; k < HPT; ++k) {
-                const float2 ww = make_float2(w[k], w[k]);
+                for (int i = 0; i < 16; ++i) acc[i] = make_float2(0.0f, 0.0f);
 #pragma unroll
-                for (int q = 0; q < NG4; ++q) {
-                    const float4 d4 = *reinterpret_cast<const float4*>(dp + k * BTP + 4 * q);
-                    acc[2 * q] = __ffma2_rn(ww, make_float2(d4.x, d4.y), acc[2 * q]);
-                    acc[2 * q + 1] = __ffma2_rn(ww, make_float2(d4.z, d4.w), acc[2 * q + 1]);
+                for (int kk = 0; kk < KH; ++kk) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        if (q0 + qq < NG4) {
+                            const float4 d4 = *reinterpret_cast<const float4*>(dp + kk * BTP + 4 * (q0 + qq));
+                            acc[4 * qq + 0] = __ffma2_rn(make_float2(d4.x, d4.x), w2[kk], acc[4 * qq + 0]);
+                            acc[4 * qq + 1] = __ffma2_rn(make_float2(d4.y, d4.y), w2[kk], acc[4 * qq + 1]);
+                            acc[4 * qq + 2] = __ffma2_rn(make_float2(d4.z, d4.z), w2[kk], acc[4 * qq + 2]);
+                            acc[4 * qq + 3] = __ffma2_rn(make_float2(d4.w, d4.w), w2[kk], acc[4 * qq + 3]);
+                        }
+                    }
                 }
-            }
-            float* P = Pp + pg * BT * HP + pj;
 #pragma unroll
-            for (int i = 0; i < BT / 2; ++i) {
-                P[(2 * i) * HP] = acc[i].x;
-                P[(2 * i + 1) * HP] = acc[i].y;
+                for (int qq = 0; qq < 4; ++qq) {
+                    if (q0 + qq < NG4) {
+#pragma unroll
+                        for (int bl = 0; bl < 4; ++bl)
+                            *reinterpret_cast<float2*>(P + (size_t)(4 * (q0 + qq) + bl) * HP) = acc[4 * qq + bl];
+                    }
+                }
             }
         }
     }

@@ -160,11 +160,11 @@ __global__ void __launch_bounds__(kRuThreads, 1)
     for (int t = 0; t < T; ++t) {
         const float* hcur = hs + ((t & 1) * NGRP + grp) * R * RS;           // h_{t-1}: read
         float* hnxt = hs + (((t + 1) & 1) * NGRP + grp) * R * RS;           // h_t: written
-        WG_RU_TRACE(0);
         if (handover) {
             if (second) group_barrier(bar_x, 2 * NG);
             else if (t > 0) group_barrier(bar_y, 2 * NG);
         }
+        WG_RU_TRACE(0);
         // ================= product: acc[i][g] = sum_k h[i][k] * W_g[k][2p, 2p+1] =================
         float2 acc[R][3];
 #pragma unroll
