@@ -801,7 +801,7 @@ int make_train_plan(TrainPlan& tp, long long B, int T, int S, int Fi, int Fh, in
         tp.splits_ih = (int)((ktall + tp.kt_per_ih - 1) / tp.kt_per_ih);
     }
     tp.off_du = o;    o = align_up(o + (size_t)tp.rows * tp.ldu * 4);
-    tp.off_biasp = o; o = align_up(o + (size_t)tp.grid_gb * 2 * tp.LD4 * 4);
+    tp.off_biasp = o; o = align_up(o + (size_t)tp.grid_gb * 3 * tp.LD4 * 4);   // 3 partial sets per CTA (regw), else 2
     tp.off_gcnp = o;  o = align_up(o + (size_t)tp.parts_gcn * (2 * 256 + 32) * 4);
     size_t sk = (size_t)tp.splits_hh_a * 2 * H * H;
     if ((size_t)tp.splits_hh_b * H * H > sk) sk = (size_t)tp.splits_hh_b * H * H;
@@ -1281,7 +1281,7 @@ int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, c
             kern<<<tp.grid_gb, wg::kGbThreads, smem, st>>>(gates, out, d_out, w_hh, DG, biasp, B, T, H, tp.LD4, tp.HP, tp.GR);
         }
         WG_CUDA(cudaGetLastError());
-        wg::gru_bias_grad_kernel<<<(4 * H + 127) / 128, 128, 0, st>>>(biasp, tp.grid_gb * 2, H, tp.LD4, d_bih, d_bhh);
+        wg::gru_bias_grad_kernel<<<(4 * H + 127) / 128, 128, 0, st>>>(biasp, tp.grid_gb * (tp.gb_regw ? 3 : 2), H, tp.LD4, d_bih, d_bhh);
         WG_CUDA(cudaGetLastError());
     }
     const int dg_vec = (tp.LD4 % 4 == 0) && aligned16(DG);

@@ -336,8 +336,7 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
             }
         }
     };
-    // misalignment (floats) of row `row` of a tensor with row stride `stride` floats whose base misalignment is a0
-    auto misal = [](int a0, long long row, int stride) { return (a0 + (int)(row & 3) * (stride & 3)) & 3; };
+    // base misalignment (floats) of the three staged tensors; a row's own is derived from it in the gate phase
     const int aG = (int)((reinterpret_cast<uintptr_t>(gates) >> 2) & 3);
     const int aD = (int)((reinterpret_cast<uintptr_t>(dout) >> 2) & 3);
     const int aH = (int)((reinterpret_cast<uintptr_t>(out) >> 2) & 3);
@@ -346,9 +345,15 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
     fence_proxy_async_smem();   // the zero fills above are ordered before the first bulk copies
     prefetch(T - 1);
 
-    // gate-phase coordinates: hidden unit gj x every second group of 4 sequences (threads 256 .. 319 idle here)
-    const int gj = tid & 127;
-    const int gq = tid >> 7;               // 0 / 1: sequence groups gq, gq + 2, ...; 2: none
+    // gate-phase coordinates: hidden unit gj x every third group of 4 sequences (3 x HPT threads)
+    const int gq = tid / HPT;              // 0 .. 2: sequence groups gq, gq + 3, ...; 3: none
+    const int gj = tid - gq * HPT;
+    const bool gate_thread = gq < 3 && gj < H;
+    const long long left = B - b0;
+    const int nvalid = left >= BT ? BT : (int)left;       // sequences of this CTA that exist
+    const unsigned dg_seq = (unsigned)T * (unsigned)LD4;  // floats between consecutive sequences of DG
+    const int tm = T & 3, hm = H & 3;
+    const int r00 = (int)((b0 * T) & 3);
     float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 
     for (int t = T - 1; t >= 0; --t) {
@@ -356,24 +361,29 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
         __syncthreads();   // the previous product's partials (and thread-written slots) are visible
 
         // ================= gate phase =================
-        if (gq < 2 && gj < H) {
+        if (gate_thread) {
+            float* dgt = DG + ((size_t)b0 * T + t) * LD4 + gj;   // this step's DG row of the CTA's first sequence
+            const int r0 = (r00 + t) & 3;                        // (row of sequence 0) mod 4
+            const float* sgp = stG + aG + gj;                    // gate rows: stride LD4 is a multiple of 4
 #pragma unroll
-            for (int grp = 0; grp < (NG4 + 1) / 2; ++grp) {
-                const int g4 = gq + 2 * grp;
+            for (int grp = 0; grp < (NG4 + 2) / 3; ++grp) {
+                const int g4 = gq + 3 * grp;
                 if (g4 < NG4) {
                     float dr[4], dz_[4], dnr[4];
 #pragma unroll
                     for (int bl = 0; bl < 4; ++bl) {
                         const int b = g4 * 4 + bl;
                         const int o = b * HP + gj;
-                        const long long row = (b0 + b) * T + t;
-                        const float* sg = stG + b * SG + misal(aG, row, LD4) + gj;
-                        const float g = ((stD[b * SR + misal(aD, row, H) + gj] + Dd[o]) + (Pp[o] + Pp[BT * HP + o])) +
+                        const int rl = (r0 + b * tm) & 3;                          // row mod 4
+                        const int mD = (aD + rl * hm) & 3;
+                        const int mH = t > 0 ? (aH + ((rl + 3) & 3) * hm) & 3 : 0;  // row - 1
+                        const float* sg = sgp + b * SG;
+                        const float g = ((stD[b * SR + mD + gj] + Dd[o]) + (Pp[o] + Pp[BT * HP + o])) +
                                         ((Pp[2 * BT * HP + o] + Pp[3 * BT * HP + o]) +
                                          (Pp[4 * BT * HP + o] + Pp[5 * BT * HP + o]));
                         const float r = sg[0], z = sg[H];
                         const float n = sg[2 * H], hn = sg[3 * H];
-                        const float hp = stH[b * SR + (t > 0 ? misal(aH, row - 1, H) : 0) + gj];
+                        const float hp = stH[b * SR + mH + gj];
                         const float dn = g * (1.0f - z);
                         const float dz = g * (hp - n);
                         const float da_n = dn * (1.0f - n * n);
@@ -382,12 +392,12 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
                         const float da_nr = da_n * r;
                         Dd[o] = g * z;
                         dr[bl] = da_r; dz_[bl] = da_z; dnr[bl] = da_nr;
-                        if (b0 + b < B) {
-                            float* dg = DG + ((size_t)(b0 + b) * T + t) * LD4;
-                            dg[gj] = da_r;
-                            dg[H + gj] = da_z;
-                            dg[2 * H + gj] = da_n;
-                            dg[3 * H + gj] = da_nr;
+                        if (b < nvalid) {
+                            float* dg = dgt + (size_t)b * dg_seq;
+                            dg[0] = da_r;
+                            dg[H] = da_z;
+                            dg[2 * H] = da_n;
+                            dg[3 * H] = da_nr;
                         }
                         bsum[0] += da_r; bsum[1] += da_z; bsum[2] += da_n; bsum[3] += da_nr;
                     }
@@ -436,9 +446,9 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
         }
     }
 
-    // ---- per-CTA column sums of DG: bias_part[(cta * 2 + gq)][LD4] ----
-    if (gq < 2 && gj < H) {
-        float* bp = bias_part + ((size_t)blockIdx.x * 2 + gq) * LD4;
+    // ---- per-CTA column sums of DG: bias_part[(cta * 3 + gq)][LD4] ----
+    if (gate_thread) {
+        float* bp = bias_part + ((size_t)blockIdx.x * 3 + gq) * LD4;
         bp[gj] = bsum[0];
         bp[H + gj] = bsum[1];
         bp[2 * H + gj] = bsum[2];
