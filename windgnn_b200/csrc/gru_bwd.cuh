@@ -245,13 +245,14 @@ __host__ __device__ constexpr int gru_bwd_regw_btp(int BT) { return ((BT / 4) % 
 // so element j of the row sits at slot[m + j], m = the row's misalignment in floats (0 .. 3)
 __host__ __device__ constexpr int gru_bwd_regw_sg(int HPT) { return 4 * HPT + 4; }   // 4H floats + m, rounded up to 4
 __host__ __device__ constexpr int gru_bwd_regw_sr(int HPT) { return HPT + 4; }       // H floats + m, rounded up to 4
+__host__ __device__ constexpr int gru_bwd_regw_nbuf(int BT) { return BT <= 8 ? 2 : 1; }   // staging buffers
 __host__ __device__ inline size_t gru_bwd_regw_smem_floats(int HPT, int BT) {
     return 3 * (size_t)HPT * gru_bwd_regw_btp(BT)      // dgh [3][HPT][BTP]
            + (size_t)BT * HPT                          // D = g z
            + 6 * (size_t)BT * HPT                      // P: the six (gate, k-half) partials of dgh . W_hh
-           + (size_t)BT * gru_bwd_regw_sg(HPT)         // staged gate rows [r|z|n|hn] of one step
-           + 2 * (size_t)BT * gru_bwd_regw_sr(HPT)     // staged dout and h_prev rows
-           + 4;                                        // mbarrier
+           + (size_t)gru_bwd_regw_nbuf(BT) * BT * (gru_bwd_regw_sg(HPT) + 2 * gru_bwd_regw_sr(HPT))   // staged rows:
+                                                       // [r|z|n|hn], dout and h_prev of one step, per buffer
+           + 4;                                        // mbarriers
 }
 
 template <int BT, int HPT>
@@ -268,10 +269,12 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
     float* Dd = dgh + 3 * HPT * BTP;          // [BT][HP]
     float* Pp = Dd + BT * HP;                 // [6][BT][HP]   slot = gate * 2 + k-half
     constexpr int SG = gru_bwd_regw_sg(HPT), SR = gru_bwd_regw_sr(HPT);
-    float* stG = Pp + 6 * BT * HP;            // [BT][SG]  gate rows
-    float* stD = stG + BT * SG;               // [BT][SR]  dout rows
-    float* stH = stD + BT * SR;               // [BT][SR]  h_prev rows
-    uint64_t* sbar = reinterpret_cast<uint64_t*>(stH + BT * SR);
+    // staging buffers: step t uses buffer t % NBUF and is fetched NBUF steps ahead.  Small CTAs (short products)
+    // need the second buffer to cover the global-memory latency; at 16 / 28 sequences the product covers it.
+    constexpr int NBUF = gru_bwd_regw_nbuf(BT);
+    constexpr int SBUF = BT * (SG + 2 * SR);  // floats per staging buffer
+    float* stage0 = Pp + 6 * BT * HP;         // [NBUF] x { [BT][SG] gate rows, [BT][SR] dout rows, [BT][SR] h_prev rows }
+    uint64_t* sbar0 = reinterpret_cast<uint64_t*>(stage0 + NBUF * SBUF);   // [NBUF]
 
     const int tid = threadIdx.x;
     const long long b0 = (long long)blockIdx.x * BT;
@@ -291,9 +294,9 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
 
     for (int e = tid; e < 3 * HPT * BTP; e += kGrwThreads) dgh[e] = 0.0f;
     for (int e = tid; e < 7 * BT * HP; e += kGrwThreads) Dd[e] = 0.0f;      // D and the partials
-    for (int e = tid; e < BT * (SG + 2 * SR); e += kGrwThreads) stG[e] = 0.0f;
+    for (int e = tid; e < NBUF * SBUF; e += kGrwThreads) stage0[e] = 0.0f;
     if (tid == 0) {
-        mbar_init(sbar, 3 * BT);
+        for (int i = 0; i < NBUF; ++i) mbar_init(&sbar0[i], 3 * BT);
         fence_mbar_init();
     }
 
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
     // last row at most), and h_prev at t = 0, are written by the thread itself.
     const int skind = tid / BT, sb = tid - skind * BT;
     const size_t n_rows = (size_t)B * T;
-    auto stage_row = [&](float* slot, const float* base, size_t total, size_t g0, int n) {
+    auto stage_row = [&](uint64_t* sbar, float* slot, const float* base, size_t total, size_t g0, int n) {
         const int m = (int)((reinterpret_cast<uintptr_t>(base + g0) >> 2) & 3);
         const int L = (m + n + 3) & ~3;
         if (g0 >= (size_t)m && g0 - m + L <= total) {
@@ -317,17 +320,22 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
         }
     };
     auto prefetch = [&](int t) {
-        if (tid < 3 * BT) {
+        if (tid < 3 * BT && t >= 0) {
+            const int buf = t % NBUF;
+            uint64_t* sbar = &sbar0[buf];
+            float* stG = stage0 + buf * SBUF;
+            float* stD = stG + BT * SG;
+            float* stH = stD + BT * SR;
             if (b0 + sb >= B) {
                 mbar_arrive(sbar);   // no such sequence: its slots stay zero
             } else {
                 const size_t row = (size_t)(b0 + sb) * T + t;
                 if (skind == 0) {
-                    stage_row(stG + sb * SG, gates, n_rows * LD4, row * LD4, 4 * H);
+                    stage_row(sbar, stG + sb * SG, gates, n_rows * LD4, row * LD4, 4 * H);
                 } else if (skind == 1) {
-                    stage_row(stD + sb * SR, dout, n_rows * H, row * H, H);
+                    stage_row(sbar, stD + sb * SR, dout, n_rows * H, row * H, H);
                 } else if (t > 0) {
-                    stage_row(stH + sb * SR, out, n_rows * H, (row - 1) * H, H);   // h_prev = out[b, t - 1]
+                    stage_row(sbar, stH + sb * SR, out, n_rows * H, (row - 1) * H, H);   // h_prev = out[b, t - 1]
                 } else {
                     for (int j = 0; j < SR; ++j) stH[sb * SR + j] = 0.0f;          // h_{-1} = 0
                     fence_proxy_async_smem();
@@ -343,7 +351,8 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
 
     __syncthreads();
     fence_proxy_async_smem();   // the zero fills above are ordered before the first bulk copies
-    prefetch(T - 1);
+#pragma unroll
+    for (int i = 1; i <= NBUF; ++i) prefetch(T - i);
 
     // gate-phase coordinates: hidden unit gj x every third group of 4 sequences (3 x HPT threads)
     const int gq = tid / HPT;              // 0 .. 2: sequence groups gq, gq + 3, ...; 3: none
@@ -357,7 +366,12 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
     float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 
     for (int t = T - 1; t >= 0; --t) {
-        mbar_wait(sbar, (unsigned)((T - 1 - t) & 1));   // staged inputs of step t have landed
+        const int buf = t % NBUF;
+        const float* stG = stage0 + buf * SBUF;
+        const float* stD = stG + BT * SG;
+        const float* stH = stD + BT * SR;
+        // staged inputs of step t have landed: the buffer's uses are steps t, t + NBUF, ... counted from T - 1 down
+        mbar_wait(&sbar0[buf], (unsigned)(((T - 1 - t) / NBUF) & 1));
         __syncthreads();   // the previous product's partials (and thread-written slots) are visible
 
         // ================= gate phase =================
@@ -410,7 +424,7 @@ __global__ void __launch_bounds__(kGrwThreads, 1)
         }
         __syncthreads();   // dgh complete; the staged inputs are free
         if (t == 0) break;
-        prefetch(t - 1);   // lands during the product
+        prefetch(t - NBUF);   // into the buffer this step has just finished with
 
         // ===== P[g][kh] = dgh[g][k-half] . W_hh[g][k-half] (this thread: gate pg, half pkh, unit pair pp, all sequences) =====
         if (prod_thread) {
