@@ -500,14 +500,12 @@ int recur_u_pick_r(long long Bc, int ngrp) {
     }
     return best;
 }
-// FMA-pipe hand-over between the two groups of a scheduler (recur_unit.cuh).  Measured (scripts/handover_ab.py,
-// profiles/r02_handover_ab.json): H = 21 (one warp per group, gate-dominated steps) 0.395 -> 0.358 ms at 4096
-// sequences; H = 102 (two warps per group) within +-5 % either way — so it is on for one-warp groups only.
-// WG_RU_HANDOVER=0 / 1 overrides (results are identical either way).
+// FMA-pipe hand-over between the two one-warp groups of a scheduler (recur_unit.cuh).  Measured
+// (scripts/handover_ab.py, profiles/r02_handover_ab.json): H = 21, 4096 sequences: 0.395 -> 0.358 ms.  Two-warp
+// groups (H = 102) own their scheduler and need none.  WG_RU_HANDOVER=0 switches it off (results are identical).
 bool recur_handover(int wpg) {
     const char* e = getenv("WG_RU_HANDOVER");
-    if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
-    return wpg == 1;
+    return wpg == 1 && !(e && e[0] == '0');
 }
 bool recur_unit_applies(const Plan& p) {
     return !force_legacy() && wg::recur_u_applies(p.H) &&

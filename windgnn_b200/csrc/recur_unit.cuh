@@ -84,12 +84,11 @@ __global__ void __launch_bounds__(kRuThreads, 1)
                           float* __restrict__ gsave, int ldsave, int handover) {
     constexpr int NGRP = kRuWarps / WPG;   // groups per CTA
     constexpr int NG = WPG * 32;           // threads per group
-    // Hand-over of the FMA pipe (handover != 0; the launcher turns it on for one-warp groups).  Warp w issues
-    // on scheduler w % 4, so groups g and g + NGRP/2 share their schedulers.  With the hand-over the second
-    // group starts its product when the first has finished its own, so one group's gate phase (MUFU, stores)
-    // runs under the other's product: barrier X = "first group's product done", Y = "second group's product
-    // done" (arrive = signal, sync = wait).  Measured: H = 21 0.395 -> 0.358 ms at 4096 sequences; H = 102
-    // (two-warp groups, product-dominated steps) 1.164 -> 1.148 ms at R = 7 but 5 % slower at R = 4 and 8.
+    // Hand-over of the FMA pipe (handover != 0; one-warp groups only).  Warp w issues on scheduler w % 4, so the
+    // one-warp groups g and g + NGRP/2 share a scheduler.  With the hand-over the second group starts its product
+    // when the first has finished its own, so one group's gate phase (MUFU, stores) runs under the other's
+    // product: barrier X = "first group's product done", Y = "second group's product done" (arrive = signal,
+    // sync = wait).  Measured: H = 21 0.395 -> 0.358 ms at 4096 sequences.
     constexpr int HALF = NGRP / 2;
     constexpr int kBarBase = WPG == 1 ? 1 : 1 + NGRP;   // WPG == 1: the group barrier is a __syncwarp
     extern __shared__ __align__(16) float smem[];
@@ -103,8 +102,12 @@ __global__ void __launch_bounds__(kRuThreads, 1)
     uint64_t* gbar = reinterpret_cast<uint64_t*>(bns + round_up(HP2, 4));   // [NGRP]
 
     const int tid = threadIdx.x;
-    const int grp = tid / NG;
-    const int p = tid - grp * NG;          // unit pair of this thread
+    // warp w issues on scheduler w % 4.  Two-warp groups take warps g and g + 4: BOTH warps of a group then sit on
+    // one scheduler, which they have to themselves — they run the product together (two warps saturate the FMA
+    // pipe, one does not: 2.2 vs 3 cycles per FFMA2) and reach the group barrier together.  (Warps 2g, 2g + 1:
+    // each warp shares its scheduler with another group's warp; the skew cost 1.1 K cycles of barrier wait per step.)
+    const int grp = WPG == 2 ? ((tid >> 5) & (NGRP - 1)) : tid / NG;
+    const int p = WPG == 2 ? ((tid >> 5) / NGRP) * 32 + (tid & 31) : tid - grp * NG;   // unit pair of this thread
     const bool second = grp >= HALF;
     const int bar_x = kBarBase + 2 * (grp - (second ? HALF : 0)), bar_y = bar_x + 1;
     const bool active = p < NS;
