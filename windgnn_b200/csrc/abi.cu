@@ -824,8 +824,7 @@ int splitk_gemm(const wg::SgOperand& A, const wg::SgOperand& Bo, long long M, in
     wg::sgemm_kernel<<<grid, wg::kSgThreads, wg::kSgSmemBytes, st>>>(A, Bo, part, N, M, N, K, kper);
     WG_CUDA(cudaGetLastError());
     const long long total = M * N;
-    const unsigned rgrid = (unsigned)((total + 255) / 256 < 4 * wg::kNumSMs ? (total + 255) / 256 : 4 * wg::kNumSMs);
-    wg::sg_reduce_kernel<<<rgrid, 256, 0, st>>>(part, splits, M, N, out, s_m, s_n, N);
+    wg::sg_reduce_kernel<<<(unsigned)((total * 8 + 255) / 256), 256, 0, st>>>(part, splits, M, N, out, s_m, s_n, N);
     WG_CUDA(cudaGetLastError());
     return WG_OK;
 }
@@ -1315,7 +1314,7 @@ int wg_gcn_gru_backward_f32(const float* adj, const float* x, const float* w1, c
         WG_CUDA(cudaGetLastError());
         // d_wih[g][i] = sum_z part[z][i][g]
         const long long total = (long long)p.G * p.I;
-        wg::sg_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(skp, tp.splits_ih, p.I, p.G, d_wih, 1, p.I,
+        wg::sg_reduce_kernel<<<(unsigned)((total * 8 + 255) / 256), 256, 0, st>>>(skp, tp.splits_ih, p.I, p.G, d_wih, 1, p.I,
                                                                              a.ldc);
         WG_CUDA(cudaGetLastError());
     }
