@@ -195,7 +195,8 @@ __device__ __forceinline__ void gb2_block(float* __restrict__ ra, float* __restr
     unsigned m1[NPW];   // bit f: G1[s][f] > 0, bit 16 + f: G1[s+1][f] > 0
 
     // ---- P1: AX = A.X (own stations) -> ra ; G1 = relu(AX.W1 + b1) -> rb ----
-    gr_aggregate<NPW, false>(acc, rb + (size_t)r * in_cols, adjT, astride, S, (in_cols & 1) == 0);
+    if ((in_cols & 1) == 0) gr_aggregate<NPW, false, true>(acc, rb + (size_t)r * in_cols, adjT, astride, S);
+    else gr_aggregate<NPW, false, false>(acc, rb + (size_t)r * in_cols, adjT, astride, S);
     __syncthreads();   // every read of the X block is done: rb becomes the G1 slab
     gb2_store_acc<NPW>(ra + (size_t)r * RS, acc, s0, s_end, 1.0f);
     {

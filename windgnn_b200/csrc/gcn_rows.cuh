@@ -53,68 +53,89 @@ __host__ __device__ inline size_t gcn_rows_smem_floats(int S) {
 }
 
 // acc[p][f] = sum_{s'} x[s'][f] * (A[2p][s'], A[2p+1][s'])  for this warp's NPW station pairs.
-// PADDED: x row is [S][16] (layer-1 result) else [S][13] as it sits in HBM (`vec`: the row length S*13 is
+// PADDED: x row is [S][16] (layer-1 result) else [S][13] as it sits in HBM (VEC: the row length S*13 is
 // even, so every row base is 8-byte aligned and the loads are 8 bytes wide where the offset is even).
-template <int NPW, bool PADDED>
+// The operands of step s'+1 are loaded BEFORE the FMAs of step s' are issued (two register fragments): with two
+// warps per scheduler the ~30 cycles from LDS to the first dependent FFMA2 were exposed once per step (ncu:
+// 11 % of the samples waiting on shared-memory data).  VEC is a template parameter so that the loop body has no
+// branch (the r02 body branched on it, which kept the loads of a step behind the FMAs of the previous one).
+template <int NPW>
+struct GrFrag {
+    float a[2 * ((NPW + 1) / 2) * 2];
+    float x[kGrF];
+};
+
+template <int NPW, bool PADDED, bool VEC>
 __device__ __forceinline__ void gr_aggregate(float2 (&acc)[NPW][kGrF], const float* __restrict__ xrow,
-                                             const float* __restrict__ arow, int astride, int S, bool vec) {
+                                             const float* __restrict__ arow, int astride, int S) {
 #pragma unroll
     for (int p = 0; p < NPW; ++p)
 #pragma unroll
         for (int f = 0; f < kGrF; ++f) acc[p][f] = make_float2(0.0f, 0.0f);
-    auto step = [&](int sp, auto odd_tag) {
+    auto load = [&](GrFrag<NPW>& fr, int sp, auto odd_tag) {
         constexpr bool ODD = decltype(odd_tag)::value != 0;
-        float a[2 * ((NPW + 1) / 2) * 2];
         const float* ap = arow + (size_t)sp * astride;
 #pragma unroll
         for (int q = 0; q < (NPW + 1) / 2; ++q) {
             const float4 t = *reinterpret_cast<const float4*>(ap + 4 * q);
-            a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w;
+            fr.a[4 * q] = t.x; fr.a[4 * q + 1] = t.y; fr.a[4 * q + 2] = t.z; fr.a[4 * q + 3] = t.w;
         }
-        float x[kGrF];
         if (PADDED) {
             const float* xp = xrow + sp * kGrFS;
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const float4 t = *reinterpret_cast<const float4*>(xp + 4 * q);
-                x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+                fr.x[4 * q] = t.x; fr.x[4 * q + 1] = t.y; fr.x[4 * q + 2] = t.z; fr.x[4 * q + 3] = t.w;
             }
-            x[12] = xp[12];
+            fr.x[12] = xp[12];
         } else {
             const float* xp = xrow + sp * kGrF;
-            if (!vec) {   // odd row length (odd S): the rows are only 4-byte aligned
+            if (!VEC) {   // odd row length (odd S): the rows are only 4-byte aligned
 #pragma unroll
-                for (int f = 0; f < kGrF; ++f) x[f] = xp[f];
+                for (int f = 0; f < kGrF; ++f) fr.x[f] = xp[f];
             } else if (!ODD) {   // even offset: pairs (0,1) .. (10,11), then 12
 #pragma unroll
                 for (int q = 0; q < 6; ++q) {
                     const float2 t = *reinterpret_cast<const float2*>(xp + 2 * q);
-                    x[2 * q] = t.x; x[2 * q + 1] = t.y;
+                    fr.x[2 * q] = t.x; fr.x[2 * q + 1] = t.y;
                 }
-                x[12] = xp[12];
+                fr.x[12] = xp[12];
             } else {      // odd offset: 0, then pairs (1,2) .. (11,12)
-                x[0] = xp[0];
+                fr.x[0] = xp[0];
 #pragma unroll
                 for (int q = 0; q < 6; ++q) {
                     const float2 t = *reinterpret_cast<const float2*>(xp + 1 + 2 * q);
-                    x[1 + 2 * q] = t.x; x[2 + 2 * q] = t.y;
+                    fr.x[1 + 2 * q] = t.x; fr.x[2 + 2 * q] = t.y;
                 }
             }
         }
+    };
+    auto fma = [&](const GrFrag<NPW>& fr) {
 #pragma unroll
         for (int p = 0; p < NPW; ++p) {
-            const float2 aa = make_float2(a[2 * p], a[2 * p + 1]);
+            const float2 aa = make_float2(fr.a[2 * p], fr.a[2 * p + 1]);
 #pragma unroll
-            for (int f = 0; f < kGrF; ++f) acc[p][f] = __ffma2_rn(make_float2(x[f], x[f]), aa, acc[p][f]);
+            for (int f = 0; f < kGrF; ++f) acc[p][f] = __ffma2_rn(make_float2(fr.x[f], fr.x[f]), aa, acc[p][f]);
         }
     };
+    // s' ascending, as before (the sums are bit-identical to gcn_kernel's)
+    GrFrag<NPW> f0, f1;
+    load(f0, 0, IntC<0>{});
     int sp = 0;
 #pragma unroll 1
-    for (; sp + 1 < S; sp += 2) {
-        step(sp, IntC<0>{});
-        step(sp + 1, IntC<1>{});
+    for (; sp + 2 < S; sp += 2) {
+        load(f1, sp + 1, IntC<1>{});
+        fma(f0);
+        load(f0, sp + 2, IntC<0>{});
+        fma(f1);
     }
-    if (sp < S) step(sp, IntC<0>{});
+    if (sp + 1 < S) {
+        load(f1, sp + 1, IntC<1>{});
+        fma(f0);
+        fma(f1);
+    } else {
+        fma(f0);
+    }
 }
 
 // o[p][c] = sum_f W[f][c0 + c] * acc[p][f]  for one chunk of WIDTH output features (f ascending)
@@ -136,7 +157,28 @@ __device__ __forceinline__ void gr_transform_chunk(float2 (&o)[NPW][4], const fl
     }
 }
 
-__device__ __forceinline__ float gr_relu(float u) { return u < 0.0f ? 0.0f : u; }   // NaN propagates like torch.relu
+// ReLU; NaN propagates like torch.relu.  One FMNMX.NAN instead of FSETP + FSEL (the epilogues run 884 of these per
+// row); WG_GR_EPI=0 restores the r02 epilogue for A/B runs.
+#ifndef WG_GR_EPI
+#define WG_GR_EPI 1
+#endif
+__device__ __forceinline__ float gr_relu(float u) {
+#if WG_GR_EPI
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(u));
+    return r;
+#else
+    return u < 0.0f ? 0.0f : u;
+#endif
+}
+// (o.x + b, o.y + b): one FADD2 for the two stations of a pair
+__device__ __forceinline__ float2 gr_bias(float2 o, float b) {
+#if WG_GR_EPI
+    return __fadd2_rn(o, make_float2(b, b));
+#else
+    return make_float2(o.x + b, o.y + b);
+#endif
+}
 
 // One row block through both layers for a warp that owns NPW station pairs starting at station s0.
 template <int NPW>
@@ -148,7 +190,8 @@ __device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* _
     const int in_cols = S * kGrF, RS2 = gcn_rows_rs2(S);
     float2 acc[NPW][kGrF];
     // ---- layer 1 ----
-    gr_aggregate<NPW, false>(acc, buf + (size_t)lane * in_cols, arow, astride, S, (in_cols & 1) == 0);
+    if ((in_cols & 1) == 0) gr_aggregate<NPW, false, true>(acc, buf + (size_t)lane * in_cols, arow, astride, S);
+    else gr_aggregate<NPW, false, false>(acc, buf + (size_t)lane * in_cols, arow, astride, S);
     __syncthreads();   // every warp has finished reading the input slab: the padded layer-1 result may overwrite it
     float* g1row = buf + (size_t)lane * RS2;
     auto store_g1 = [&](const float2 (&o)[NPW][4], int c0) {
@@ -158,11 +201,11 @@ __device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* _
         for (int p = 0; p < NPW; ++p) {
             const int s = s0 + 2 * p;
             float4 v0, v1;   // columns >= 13 come out as relu(0 + 0) = 0: the padding is defined
-            v0.x = gr_relu(o[p][0].x + bv[0]); v0.y = gr_relu(o[p][1].x + bv[1]);
-            v0.z = gr_relu(o[p][2].x + bv[2]); v0.w = gr_relu(o[p][3].x + bv[3]);
-            v1.x = gr_relu(o[p][0].y + bv[0]); v1.y = gr_relu(o[p][1].y + bv[1]);
-            v1.z = gr_relu(o[p][2].y + bv[2]); v1.w = gr_relu(o[p][3].y + bv[3]);
-            if (s < S) *reinterpret_cast<float4*>(g1row + s * kGrFS + c0) = v0;
+            const float2 u0 = gr_bias(o[p][0], bv[0]), u1 = gr_bias(o[p][1], bv[1]);
+            const float2 u2 = gr_bias(o[p][2], bv[2]), u3 = gr_bias(o[p][3], bv[3]);
+            v0.x = gr_relu(u0.x); v0.y = gr_relu(u1.x); v0.z = gr_relu(u2.x); v0.w = gr_relu(u3.x);
+            v1.x = gr_relu(u0.y); v1.y = gr_relu(u1.y); v1.z = gr_relu(u2.y); v1.w = gr_relu(u3.y);
+            *reinterpret_cast<float4*>(g1row + s * kGrFS + c0) = v0;   // s < S for every owned pair (pairs < ceil(S/2))
             if (s + 1 < S) *reinterpret_cast<float4*>(g1row + (s + 1) * kGrFS + c0) = v1;
         }
     };
@@ -178,7 +221,7 @@ __device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* _
     }
     __syncthreads();   // layer-1 result complete
     // ---- layer 2 ----
-    gr_aggregate<NPW, true>(acc, g1row, arow, astride, S, true);
+    gr_aggregate<NPW, true, true>(acc, g1row, arow, astride, S);
     __syncthreads();   // the slab is free: every warp holds its layer-2 aggregate in registers
     // the next block's bulk copy starts NOW and lands while this block's transform / stores run from registers
     if (next_bytes != 0 && threadIdx.x == 0) {
@@ -197,8 +240,9 @@ __device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* _
                 float* c_lo = out_col0 + (size_t)(s * kGrF + c0) * kUTileRows;
 #pragma unroll
                 for (int c = 0; c < W; ++c) {
-                    if (s < S) c_lo[(size_t)c * kUTileRows] = gr_relu(o[p][c].x + bv[c]);
-                    if (s + 1 < S) c_lo[(size_t)(kGrF + c) * kUTileRows] = gr_relu(o[p][c].y + bv[c]);
+                    const float2 u = gr_bias(o[p][c], bv[c]);
+                    c_lo[(size_t)c * kUTileRows] = gr_relu(u.x);
+                    if (s + 1 < S) c_lo[(size_t)(kGrF + c) * kUTileRows] = gr_relu(u.y);
                 }
             }
         }
