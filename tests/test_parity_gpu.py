@@ -105,7 +105,8 @@ def _random_model(S, seed, H=None):
     return m
 
 
-@pytest.mark.parametrize("S,H,B,T", [(1, 3, 5, 4), (3, 9, 33, 7), (12, 36, 70, 11), (34, 102, 65, 9), (20, 50, 31, 6)])
+@pytest.mark.parametrize("S,H,B,T", [(1, 3, 5, 4), (3, 9, 33, 7), (12, 36, 70, 11), (34, 102, 65, 9), (20, 50, 31, 6),
+                                     (33, 99, 37, 5)])
 def test_ragged_shapes_vs_oracle(S, H, B, T):
     """Batch sizes that are not multiples of the 32-sequence CTA tile, odd S / H, row tiles cut by
     the end of the batch."""
@@ -119,6 +120,22 @@ def test_ragged_shapes_vs_oracle(S, H, B, T):
         y = m.to(DEV)(torch.from_numpy(adj).to(DEV), torch.from_numpy(x).to(DEV))
     y = y.reshape(B, T, H).cpu().numpy()
     assert normalised_max_error(y, ref) <= TOL
+
+
+@pytest.mark.parametrize("S,B,T", [(34, 70, 6), (33, 45, 4), (31, 40, 3)])
+def test_gcn_generations_are_bit_identical(S, B, T, monkeypatch):
+    """gcn_rows_kernel (S = 33 / 34: four station pairs per warp plus a feature slice of the shared 17th pair;
+    S = 31: the uneven split) against the first-generation gcn_kernel: every sum keeps its order."""
+    m = _random_model(S, seed=S + B).to(DEV)
+    rng = np.random.default_rng(S * 31 + B)
+    adj = torch.from_numpy((rng.random((S, S), dtype=np.float32) / S).astype(np.float32)).to(DEV)
+    x = torch.from_numpy(rng.random((B, T, S, 13), dtype=np.float32) - 0.25).to(DEV)
+    with torch.no_grad():
+        monkeypatch.setenv("WG_FORCE_LEGACY", "1")
+        y_old = m(adj, x)
+        monkeypatch.setenv("WG_FORCE_LEGACY", "0")
+        y_new = m(adj, x)
+    assert torch.equal(y_old, y_new)
 
 
 def test_empty_batch():

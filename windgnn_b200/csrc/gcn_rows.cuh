@@ -43,12 +43,30 @@ __host__ __device__ inline bool gcn_rows_applies(int S, int Fi, int Fh, int Fo) 
     return Fi == kGrF && Fh == kGrF && Fo == kGrF && gcn_rows_warps(S) <= kGrMaxWarps && S <= 48;
 }
 __host__ __device__ inline int gcn_rows_rs2(int S) { return S * kGrFS + 4; }
+// Balanced mode (17 station pairs over 4 warps, i.e. S = 33 / 34): every warp owns 4 pairs and the 17th pair is
+// SHARED — warp w aggregates it for the feature slice 3w .. 3w + 3 and, after the barrier that follows the
+// aggregation anyway, transforms it for the same slice of output columns; the aggregate travels through a
+// [32 rows][28] exchange buffer per layer.  Every sum keeps its order (s' ascending, f ascending), so the result
+// is bit-identical to the 5/4/4/4 split, whose light warps spent 20 % of their time at the CTA barriers
+// (ncu: 16 % of all warp samples) waiting for the warp with five pairs.
+constexpr int kGrXS = 28;   // exchange row stride (floats): 13 float2, padded; 8 lanes x 16 B cover all 32 banks
+#ifndef WG_GR_BALANCED
+#define WG_GR_BALANCED 1   // 0: the 5/4/4/4 split (A/B runs)
+#endif
+__host__ __device__ inline bool gcn_rows_balanced(int S) { return WG_GR_BALANCED && ceil_div(S, 2) == 17; }
+// warp w's slice: features / output columns 3w .. 3w + 3 (0-3, 3-6, 6-9, 9-12; the boundary columns are computed
+// by two warps — the same value, stored twice — so that all four warps run ONE instruction stream: with a slice per
+// template instantiation the four warps of a CTA executed four copies of the block code and the kernel ran at
+// half speed on instruction-cache misses)
+constexpr int kGrSliceStep = 3;
+constexpr int kGrSliceW = 4;
 __host__ __device__ inline size_t gcn_rows_smem_floats(int S) {
     const int NW = gcn_rows_warps(S);
     size_t n = (size_t)S * NW * kGrAP;                 // adjW[s'][warp][12]
     n += 2 * (size_t)kGcnFS * kGcnFS + 2 * kGcnFS;     // w1, w2, b1, b2 (zero padded 16 x 16 / 16)
     const size_t in_f = (size_t)kGrRows * S * kGrF, g1_f = (size_t)kGrRows * gcn_rows_rs2(S);
     n += round_up((int)(in_f > g1_f ? in_f : g1_f), 4) + 4;   // slab block (+ mbarrier)
+    if (gcn_rows_balanced(S)) n += 2 * (size_t)kGrRows * kGrXS;   // shared-pair exchange, one buffer per layer
     return n;
 }
 
@@ -59,26 +77,40 @@ __host__ __device__ inline size_t gcn_rows_smem_floats(int S) {
 // warps per scheduler the ~30 cycles from LDS to the first dependent FFMA2 were exposed once per step (ncu:
 // 11 % of the samples waiting on shared-memory data).  VEC is a template parameter so that the loop body has no
 // branch (the r02 body branched on it, which kept the loads of a step behind the FMAs of the previous one).
-template <int NPW>
+// SHARED: balanced mode, this warp's slice of the shared pair (its adjacency pair sits behind the NPW own pairs;
+// the slice's four x values are loaded separately at the runtime offset f0 — the register copy of the row cannot
+// be indexed at run time)
+template <int NPW, bool SHARED>
 struct GrFrag {
-    float a[2 * ((NPW + 1) / 2) * 2];
+    static constexpr int NA4 = (NPW + (SHARED ? 1 : 0) + 1) / 2;   // float4 loads of adjacency values
+    float a[NA4 * 4];
     float x[kGrF];
+    float xs[kGrSliceW];
 };
 
-template <int NPW, bool PADDED, bool VEC>
-__device__ __forceinline__ void gr_aggregate(float2 (&acc)[NPW][kGrF], const float* __restrict__ xrow,
-                                             const float* __restrict__ arow, int astride, int S) {
+template <int NPW, bool PADDED, bool VEC, bool SHARED>
+__device__ __forceinline__ void gr_aggregate_x(float2 (&acc)[NPW][kGrF], float2 (&accs)[4],
+                                               const float* __restrict__ xrow, const float* __restrict__ arow,
+                                               int astride, int S, int fs0) {
+    using Frag = GrFrag<NPW, SHARED>;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) accs[j] = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int p = 0; p < NPW; ++p)
 #pragma unroll
         for (int f = 0; f < kGrF; ++f) acc[p][f] = make_float2(0.0f, 0.0f);
-    auto load = [&](GrFrag<NPW>& fr, int sp, auto odd_tag) {
+    auto load = [&](Frag& fr, int sp, auto odd_tag) {
         constexpr bool ODD = decltype(odd_tag)::value != 0;
         const float* ap = arow + (size_t)sp * astride;
 #pragma unroll
-        for (int q = 0; q < (NPW + 1) / 2; ++q) {
+        for (int q = 0; q < Frag::NA4; ++q) {
             const float4 t = *reinterpret_cast<const float4*>(ap + 4 * q);
             fr.a[4 * q] = t.x; fr.a[4 * q + 1] = t.y; fr.a[4 * q + 2] = t.z; fr.a[4 * q + 3] = t.w;
+        }
+        if constexpr (SHARED) {
+            const float* xq = xrow + sp * (PADDED ? kGrFS : kGrF) + fs0;
+#pragma unroll
+            for (int j = 0; j < kGrSliceW; ++j) fr.xs[j] = xq[j];
         }
         if (PADDED) {
             const float* xp = xrow + sp * kGrFS;
@@ -110,16 +142,21 @@ __device__ __forceinline__ void gr_aggregate(float2 (&acc)[NPW][kGrF], const flo
             }
         }
     };
-    auto fma = [&](const GrFrag<NPW>& fr) {
+    auto fma = [&](const Frag& fr) {
 #pragma unroll
         for (int p = 0; p < NPW; ++p) {
             const float2 aa = make_float2(fr.a[2 * p], fr.a[2 * p + 1]);
 #pragma unroll
             for (int f = 0; f < kGrF; ++f) acc[p][f] = __ffma2_rn(make_float2(fr.x[f], fr.x[f]), aa, acc[p][f]);
         }
+        if constexpr (SHARED) {
+            const float2 aa = make_float2(fr.a[2 * NPW], fr.a[2 * NPW + 1]);
+#pragma unroll
+            for (int j = 0; j < kGrSliceW; ++j) accs[j] = __ffma2_rn(make_float2(fr.xs[j], fr.xs[j]), aa, accs[j]);
+        }
     };
     // s' ascending, as before (the sums are bit-identical to gcn_kernel's)
-    GrFrag<NPW> f0, f1;
+    Frag f0, f1;
     load(f0, 0, IntC<0>{});
     int sp = 0;
 #pragma unroll 1
@@ -136,6 +173,36 @@ __device__ __forceinline__ void gr_aggregate(float2 (&acc)[NPW][kGrF], const flo
     } else {
         fma(f0);
     }
+}
+
+template <int NPW, bool PADDED, bool VEC>
+__device__ __forceinline__ void gr_aggregate(float2 (&acc)[NPW][kGrF], const float* __restrict__ xrow,
+                                             const float* __restrict__ arow, int astride, int S) {
+    float2 unused[4];
+    gr_aggregate_x<NPW, PADDED, VEC, false>(acc, unused, xrow, arow, astride, S, 0);
+}
+
+// The shared pair's transform for this warp's slice of output columns: o[j] = sum_f W[f][c0 + j] * agg[f]
+// (f ascending), agg = the pair's 13 aggregated features of this lane's row, read back from the exchange row.
+__device__ __forceinline__ void gr_transform_shared(float2 (&o)[kGrSliceW], const float* __restrict__ xrow,
+                                                    const float* __restrict__ Wn, int c0) {
+    float2 agg[kGrF + 1];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(xrow + 4 * q);
+        agg[2 * q] = make_float2(t.x, t.y);
+        agg[2 * q + 1] = make_float2(t.z, t.w);
+    }
+#pragma unroll
+    for (int j = 0; j < kGrSliceW; ++j) o[j] = make_float2(0.0f, 0.0f);
+    const float* wp = Wn + c0;
+#pragma unroll
+    for (int f = 0; f < kGrF; ++f)
+#pragma unroll
+        for (int j = 0; j < kGrSliceW; ++j) {
+            const float wv = wp[f * kGcnFS + j];
+            o[j] = __ffma2_rn(make_float2(wv, wv), agg[f], o[j]);
+        }
 }
 
 // o[p][c] = sum_f W[f][c0 + c] * acc[p][f]  for one chunk of WIDTH output features (f ascending)
@@ -181,17 +248,31 @@ __device__ __forceinline__ float2 gr_bias(float2 o, float b) {
 }
 
 // One row block through both layers for a warp that owns NPW station pairs starting at station s0.
-template <int NPW>
+// SHARED (balanced mode): additionally this warp's feature / column slice f0 .. f0 + 3 of the shared pair
+// (stations 32, 33); xch = this lane's two exchange rows (layer 1, layer 2: kGrRows * kGrXS floats apart).
+template <int NPW, bool SHARED>
 __device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* __restrict__ arow, int astride,
                                          const float* __restrict__ w1d, const float* __restrict__ b1s,
                                          const float* __restrict__ w2d, const float* __restrict__ b2s, int S, int s0,
                                          int lane, bool row_ok, float* __restrict__ out_col0, int ldo, bool pad_warp,
-                                         const float* __restrict__ next_src, unsigned next_bytes, uint64_t* bar) {
+                                         const float* __restrict__ next_src, unsigned next_bytes, uint64_t* bar,
+                                         float* __restrict__ xch, int f0) {
+    constexpr int SNF = kGrSliceW;
+    constexpr int SS = 32;   // the shared pair's first station (pair 16)
+    const int SF0 = f0;
     const int in_cols = S * kGrF, RS2 = gcn_rows_rs2(S);
     float2 acc[NPW][kGrF];
+    float2 accs[4];
+    auto put_shared = [&](float* row) {   // this warp's slice of the shared pair's aggregate -> exchange row
+#pragma unroll
+        for (int j = 0; j < SNF; ++j) *reinterpret_cast<float2*>(row + 2 * (SF0 + j)) = accs[j];
+    };
     // ---- layer 1 ----
-    if ((in_cols & 1) == 0) gr_aggregate<NPW, false, true>(acc, buf + (size_t)lane * in_cols, arow, astride, S);
-    else gr_aggregate<NPW, false, false>(acc, buf + (size_t)lane * in_cols, arow, astride, S);
+    if ((in_cols & 1) == 0)
+        gr_aggregate_x<NPW, false, true, SHARED>(acc, accs, buf + (size_t)lane * in_cols, arow, astride, S, f0);
+    else
+        gr_aggregate_x<NPW, false, false, SHARED>(acc, accs, buf + (size_t)lane * in_cols, arow, astride, S, f0);
+    if (SHARED) put_shared(xch);
     __syncthreads();   // every warp has finished reading the input slab: the padded layer-1 result may overwrite it
     float* g1row = buf + (size_t)lane * RS2;
     auto store_g1 = [&](const float2 (&o)[NPW][4], int c0) {
@@ -219,9 +300,20 @@ __device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* _
         gr_transform_chunk<NPW, 1>(o, acc, w1d, 12);   // feature 12 (kGrF == 13)
         store_g1(o, 12);
     }
+    if (SHARED) {   // shared pair, this warp's output columns SF0 .. SF0 + SNF - 1
+        float2 o[4];
+        gr_transform_shared(o, xch, w1d, SF0);
+#pragma unroll
+        for (int j = 0; j < SNF; ++j) {
+            const float2 u = gr_bias(o[j], b1s[SF0 + j]);
+            g1row[SS * kGrFS + SF0 + j] = gr_relu(u.x);
+            if (SS + 1 < S) g1row[(SS + 1) * kGrFS + SF0 + j] = gr_relu(u.y);
+        }
+    }
     __syncthreads();   // layer-1 result complete
     // ---- layer 2 ----
-    gr_aggregate<NPW, true, true>(acc, g1row, arow, astride, S);
+    gr_aggregate_x<NPW, true, true, SHARED>(acc, accs, g1row, arow, astride, S, f0);
+    if (SHARED) put_shared(xch + kGrRows * kGrXS);
     __syncthreads();   // the slab is free: every warp holds its layer-2 aggregate in registers
     // the next block's bulk copy starts NOW and lands while this block's transform / stores run from registers
     if (next_bytes != 0 && threadIdx.x == 0) {
@@ -257,6 +349,19 @@ __device__ __forceinline__ void gr_block(float* __restrict__ buf, const float* _
         gr_transform_chunk<NPW, 1>(o, acc, w2d, 12);
         store_u(o, 12, IntC<1>{});
     }
+    if (SHARED) {
+        float2 o[4];
+        gr_transform_shared(o, xch + kGrRows * kGrXS, w2d, SF0);
+        if (row_ok) {
+            float* c_lo = out_col0 + (size_t)(SS * kGrF + SF0) * kUTileRows;
+#pragma unroll
+            for (int j = 0; j < SNF; ++j) {
+                const float2 u = gr_bias(o[j], b2s[SF0 + j]);
+                c_lo[(size_t)j * kUTileRows] = gr_relu(u.x);
+                if (SS + 1 < S) c_lo[(size_t)(kGrF + j) * kUTileRows] = gr_relu(u.y);
+            }
+        }
+    }
     if (pad_warp && row_ok)   // zero the K padding of the projection GEMM
         for (int c = in_cols; c < ldo; ++c) out_col0[(size_t)c * kUTileRows] = 0.0f;
 }
@@ -273,7 +378,9 @@ __global__ void __launch_bounds__(kGrMaxWarps * 32, 1)
     const int in_cols = S * kGrF;
     // station pairs are dealt out as evenly as possible; the warps with one more pair are rotated
     // with the CTA's wave so that co-resident CTAs do not put their heavy warps on one scheduler
-    const int NPT = ceil_div(S, 2), base = NPT / NW, extra = NPT % NW;
+    // (balanced mode: four pairs per warp, the 17th is shared by feature slice — no heavy warp)
+    const bool balanced = gcn_rows_balanced(S);
+    const int NPT = balanced ? 16 : ceil_div(S, 2), base = NPT / NW, extra = NPT % NW;
     const int w = ((tid >> 5) + (blockIdx.x / kNumSMs) * 2) % NW;
     const int npw = base + (w < extra ? 1 : 0);
     const int p0 = w * base + (w < extra ? w : extra);
@@ -287,13 +394,15 @@ __global__ void __launch_bounds__(kGrMaxWarps * 32, 1)
     float* buf = b2s + kGcnFS;
     const size_t in_f = (size_t)kGrRows * in_cols, g1_f = (size_t)kGrRows * gcn_rows_rs2(S);
     uint64_t* bar = reinterpret_cast<uint64_t*>(buf + round_up((int)(in_f > g1_f ? in_f : g1_f), 4));
+    float* xch = reinterpret_cast<float*>(bar) + 4 + (size_t)lane * kGrXS;   // balanced mode: [2][32][28] after the mbarrier
 
     for (int e = tid; e < S * NW * kGrAP; e += nthreads) {
         const int sp = e / (NW * kGrAP), c = e % (NW * kGrAP);
         const int ww = c / kGrAP, i = c % kGrAP;
         const int wn = base + (ww < extra ? 1 : 0), ws0 = 2 * (ww * base + (ww < extra ? ww : extra));
-        const int s = ws0 + i;
-        adjW[e] = (i < 2 * wn && s < S) ? adj[(size_t)s * S + sp] : 0.0f;
+        // balanced mode: the shared pair's adjacency values follow the warp's own pairs in every warp's slot
+        const int s = i < 2 * wn ? ws0 + i : (balanced && i < 2 * wn + 2 ? 32 + (i - 2 * wn) : S);
+        adjW[e] = s < S ? adj[(size_t)s * S + sp] : 0.0f;
     }
     for (int e = tid; e < kGcnFS * kGcnFS; e += nthreads) {
         const int f = e / kGcnFS, fo = e % kGcnFS;
@@ -355,12 +464,17 @@ __global__ void __launch_bounds__(kGrMaxWarps * 32, 1)
         const bool pad_warp = w == NW - 1;
 #define WG_GR(N)                                                                                              \
     case N:                                                                                                   \
-        gr_block<N>(buf, arow, astride, w1d, b1s, w2d, b2s, S, s0, lane, row_ok, out_col0, ldo, pad_warp,     \
-                    nsrc, nbytes, bar);                                                                       \
+        gr_block<N, false>(buf, arow, astride, w1d, b1s, w2d, b2s, S, s0, lane, row_ok, out_col0, ldo,        \
+                           pad_warp, nsrc, nbytes, bar, xch, 0);                                              \
         break;
-        switch (npw) {   // warp-uniform
-            WG_GR(1) WG_GR(2) WG_GR(3) WG_GR(4) WG_GR(5)
-            default: break;
+        if (balanced) {   // one instruction stream for the four warps; the slice offset is a runtime value
+            gr_block<4, true>(buf, arow, astride, w1d, b1s, w2d, b2s, S, s0, lane, row_ok, out_col0, ldo, pad_warp,
+                              nsrc, nbytes, bar, xch, kGrSliceStep * w);
+        } else {
+            switch (npw) {   // warp-uniform
+                WG_GR(1) WG_GR(2) WG_GR(3) WG_GR(4) WG_GR(5)
+                default: break;
+            }
         }
 #undef WG_GR
         // gr_block's last barrier separates this block's reads of the slab from the next bulk copy
