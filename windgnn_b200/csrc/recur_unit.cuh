@@ -41,6 +41,11 @@ __host__ __device__ inline int recur_u_hp2(int H) { return round_up(H, 2); }
 // warps per group: a lane owns one unit pair
 __host__ __device__ inline int recur_u_wpg(int H) { return recur_u_hp2(H) / 2 <= 32 ? 1 : 2; }
 __host__ __device__ inline bool recur_u_applies(int H) { return recur_u_hp2(H) / 2 <= 64; }
+// gi tiles in flight per group.  One-warp groups (H <= 64) have a product of a few hundred cycles per step — shorter
+// than the latency of the bulk copy that brings the next step's gi — so their tile is a ring filled kRuGiRing steps
+// ahead; two-warp groups (9 K cycles of product per step, shared memory full of W_hh) keep one tile.
+constexpr int kRuGiRing = 4;
+__host__ __device__ inline int recur_u_nb(int H) { return recur_u_wpg(H) == 1 ? kRuGiRing : 1; }
 // h rows: KP floats, padded so that consecutive rows start in different 16-byte bank groups
 __host__ __device__ inline int recur_u_hs_stride(int KP) { return ((KP / 4) & 1) ? KP : KP + 4; }
 __host__ __device__ inline size_t recur_u_smem_floats(int H, int R) {
@@ -49,9 +54,9 @@ __host__ __device__ inline size_t recur_u_smem_floats(int H, int R) {
     size_t n = (size_t)KP * 3 * HP2;                          // W_hh^T as [k][gate][unit]
     n = round_up((int)n, 4);
     n += 2 * (size_t)NGRP * R * recur_u_hs_stride(KP);        // h, double buffered
-    n += (size_t)NGRP * R * GP;                               // gi tile of the current step, per group
+    n += (size_t)recur_u_nb(H) * NGRP * R * GP;               // gi tiles (ring of recur_u_nb steps), per group
     n += (size_t)round_up(HP2, 4);                            // b_hn
-    n += 2 * kRuWarps;                                        // one mbarrier per group
+    n += 2 * (size_t)NGRP * recur_u_nb(H);                    // one mbarrier per group and ring slot
     return n;
 }
 
@@ -84,6 +89,7 @@ __global__ void __launch_bounds__(kRuThreads, 1)
                           float* __restrict__ gsave, int ldsave, int handover) {
     constexpr int NGRP = kRuWarps / WPG;   // groups per CTA
     constexpr int NG = WPG * 32;           // threads per group
+    constexpr int NB = WPG == 1 ? kRuGiRing : 1;   // gi ring slots per group (recur_u_nb)
     // Hand-over of the FMA pipe (handover != 0; one-warp groups only).  Warp w issues on scheduler w % 4, so the
     // one-warp groups g and g + NGRP/2 share a scheduler.  With the hand-over the second group starts its product
     // when the first has finished its own, so one group's gate phase (MUFU, stores) runs under the other's
@@ -97,9 +103,9 @@ __global__ void __launch_bounds__(kRuThreads, 1)
     const int RS = recur_u_hs_stride(KP);
     float* Ws = smem;                                                // [KP][3][HP2]
     float* hs = Ws + round_up(KP * 3 * HP2, 4);                      // [2][NGRP * R][RS]
-    float* gis = hs + 2 * NGRP * R * RS;                             // [NGRP][R][ldg]
-    float* bns = gis + NGRP * R * ldg;                               // [HP2]
-    uint64_t* gbar = reinterpret_cast<uint64_t*>(bns + round_up(HP2, 4));   // [NGRP]
+    float* gis = hs + 2 * NGRP * R * RS;                             // [NB][NGRP][R][ldg]
+    float* bns = gis + NB * NGRP * R * ldg;                          // [HP2]
+    uint64_t* gbar = reinterpret_cast<uint64_t*>(bns + round_up(HP2, 4));   // [NGRP][NB]
 
     const int tid = threadIdx.x;
     // warp w issues on scheduler w % 4.  Two-warp groups take warps g and g + 4: BOTH warps of a group then sit on
@@ -126,25 +132,29 @@ __global__ void __launch_bounds__(kRuThreads, 1)
         for (int e = tid; e < n4; e += kRuThreads) dst[e] = __ldg(src + e);
     }
     for (int e = tid; e < 2 * NGRP * R * RS; e += kRuThreads) hs[e] = 0.0f;
-    for (int e = tid; e < NGRP * R * ldg; e += kRuThreads) gis[e] = 0.0f;
+    for (int e = tid; e < NB * NGRP * R * ldg; e += kRuThreads) gis[e] = 0.0f;
     for (int e = tid; e < HP2; e += kRuThreads) bns[e] = e < H ? __ldg(bhn + e) : 0.0f;
-    if (tid < NGRP) mbar_init(&gbar[tid], 1);
+    if (tid < NGRP * NB) mbar_init(&gbar[tid], 1);
     if (tid == 0) fence_mbar_init();
 
-    // gi(t) of the group's sequences: one bulk async copy per row (ldg * 4 bytes, 16-byte multiple) into the
-    // group's tile, completion counted on the group's mbarrier.  Issued by one thread AFTER the group barrier
-    // that ends step t-1, i.e. when every thread of the group has read gi(t-1).
-    float* gi_tile = gis + grp * R * ldg;
+    // gi(t) of the group's sequences: one bulk async copy per row (ldg * 4 bytes, 16-byte multiple) into slot
+    // t % NB of the group's tile ring, completion counted on that slot's mbarrier.  Issued by one thread AFTER the
+    // group barrier that ends step t - NB, i.e. when every thread of the group has read gi(t - NB).
+    float* gi_ring = gis + grp * R * ldg;        // slot stride: NGRP * R * ldg
+    uint64_t* gi_bar = gbar + grp * NB;
     auto fetch_gi = [&](int t) {
         if (nvalid > 0) {
-            mbar_expect_tx(&gbar[grp], (unsigned)(nvalid * ldg * 4));
+            const int slot = NB == 1 ? 0 : t % NB;
+            float* tile = gi_ring + slot * (NGRP * R * ldg);
+            mbar_expect_tx(&gi_bar[slot], (unsigned)(nvalid * ldg * 4));
             for (int i = 0; i < nvalid; ++i)
-                bulk_g2s(gi_tile + i * ldg, GI + ((size_t)(b0 + i) * T + t) * ldg, (unsigned)(ldg * 4), &gbar[grp]);
+                bulk_g2s(tile + i * ldg, GI + ((size_t)(b0 + i) * T + t) * ldg, (unsigned)(ldg * 4), &gi_bar[slot]);
         }
     };
 
     __syncthreads();   // zero fills and barrier inits are done before any async copy may land
-    if (p == 0) fetch_gi(0);
+    if (p == 0)
+        for (int t = 0; t < NB && t < T; ++t) fetch_gi(t);
 
     float2 hprev[R];   // h_{t-1} of this thread's items
 #pragma unroll
@@ -226,7 +236,9 @@ __global__ void __launch_bounds__(kRuThreads, 1)
         }
         WG_RU_TRACE(1);
         // ================= gates, straight from the accumulators =================
-        if (nvalid > 0) mbar_wait(&gbar[grp], (unsigned)(t & 1));   // gi(t) has landed
+        const int slot = NB == 1 ? 0 : t % NB;
+        const float* gi_tile = gi_ring + slot * (NGRP * R * ldg);
+        if (nvalid > 0) mbar_wait(&gi_bar[slot], (unsigned)((t / NB) & 1));   // gi(t) has landed
         float2 gi[3][R];
 #pragma unroll
         for (int g = 0; g < 3; ++g)
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(kRuThreads, 1)
         WG_RU_TRACE(3);
         if (WPG == 1) __syncwarp();
         else group_barrier(1 + grp, NG);
-        if (p == 0 && t + 1 < T) fetch_gi(t + 1);   // lands during the next product
+        if (p == 0 && t + NB < T) fetch_gi(t + NB);   // refills the slot just read; lands during the next product(s)
         WG_RU_TRACE(4);
     }
 }
