@@ -530,10 +530,13 @@ int launch_recur_unit(const Plan& p, void* ws, float* out, long long Bc, cudaStr
     const int wpg = wg::recur_u_wpg(p.H);
     int r = recur_u_pick_r(Bc, wg::kRuWarps / wpg);
     while (r > wg::kRuMinR && wg::recur_u_smem_floats(p.H, r) * 4 > (size_t)wg::kMaxSmemOptin) --r;
-    // H = 102 (the shipped 34-station model, 3 x 34) has its own instantiation with compile-time strides
+    // H = 102 and H = 21 (the shipped 34- and 7-station models, 3 x S) have their own instantiations with
+    // compile-time strides; for the odd H = 21 this also folds the alignment branches of the gate phase
+    // (ncu: 55 % of the generic kernel's samples sat in that branchy code at H = 21)
 #define WG_RU(RR)                                                                                          \
     case RR:                                                                                               \
         if (p.H == 102) return launch_recur_unit_t<RR, 2, SAVE, 102>(p, ws, out, Bc, st, gsave, ldsave);   \
+        if (p.H == 21) return launch_recur_unit_t<RR, 1, SAVE, 21>(p, ws, out, Bc, st, gsave, ldsave);     \
         return wpg == 1 ? launch_recur_unit_t<RR, 1, SAVE, 0>(p, ws, out, Bc, st, gsave, ldsave)           \
                         : launch_recur_unit_t<RR, 2, SAVE, 0>(p, ws, out, Bc, st, gsave, ldsave);
     switch (r) {
